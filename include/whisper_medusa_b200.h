@@ -1,0 +1,125 @@
+/*
+ * whisper_medusa_b200 -- C ABI of the B200-native Whisper-Medusa decode path.
+ *
+ * The reference (aiola-lab/whisper-medusa) is pure Python and has no FFI of its own; the
+ * boundary it exposes for this path is the Python surface of
+ *   whisper_medusa/models/model.py:213  class WhisperMedusaModel
+ *     :265-291   from_pretrained(path)          -> wm_create + wm_tensor_info/wm_load_weights
+ *     :1419-1449 generate(input_features, ...)  -> wm_encode_mel / wm_encode_pcm + wm_generate
+ *     :1223-1347 forward(...).logits            -> wm_last_logits (parity tap)
+ * Each entry point below names the reference lines it replaces.  The Python host
+ * (whisper_medusa_b200/model.py) binds exactly these symbols with ctypes; INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host buffer; the handle
+ * owns all device memory (unless weights are adopted with wm_adopt_weights); one handle =
+ * one CUDA device + one stream; a handle is not thread-safe, distinct handles are
+ * independent.  Every function returns 0 on success or a negative wm_status.
+ */
+#ifndef WHISPER_MEDUSA_B200_H_
+#define WHISPER_MEDUSA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wm_handle wm_handle;
+
+typedef enum wm_status {
+  WM_OK = 0,
+  WM_ERR_INVALID = -1,      /* bad argument / unsupported configuration            */
+  WM_ERR_CUDA = -2,         /* a CUDA runtime call failed (see wm_last_error)      */
+  WM_ERR_STATE = -3,        /* call order violated (e.g. generate before encode)   */
+  WM_ERR_UNSUPPORTED = -4,  /* valid in the reference but not implemented here     */
+  WM_ERR_NOMEM = -5
+} wm_status;
+
+/* Shape of the model: the fields of MedusaConfig the path reads
+ * (reference whisper_medusa/utils/config_and_args.py:17-62). */
+typedef struct wm_config {
+  int32_t vocab_size;
+  int32_t d_model;
+  int32_t n_heads;            /* encoder == decoder attention heads; head_dim must be 64 */
+  int32_t ffn_dim;
+  int32_t enc_layers;
+  int32_t dec_layers;
+  int32_t n_mels;             /* 80 */
+  int32_t max_source_positions; /* 1500 */
+  int32_t max_target_positions; /* 448 */
+  int32_t medusa_num_heads;   /* K */
+  int32_t medusa_block;       /* 0 = "base_head" (Medusa-Linear), 1 = "medusa_block" */
+} wm_config;
+
+/* What _medusa_greedy_search reads from the generation config and kwargs
+ * (reference model.py:404-835; medusa_utils.py:14-18). */
+typedef struct wm_gen_params {
+  int32_t max_length;          /* generation_config.max_length (448) */
+  int32_t eos_token_id;
+  int32_t pad_token_id;
+  int32_t begin_index;         /* SuppressTokensAtBegin begin_index = len(prompt) */
+  float temperature;           /* generate() forces 1.0 (model.py:1878-1881); 0 = exact-match acceptance */
+  float posterior_threshold;   /* 0.09 */
+  float posterior_alpha;       /* 0.3  */
+  int32_t penalty_start;       /* ExponentialDecayLengthPenalty start_index, <0 = off */
+  float penalty_factor;
+  int32_t max_iters;           /* 0 = run to completion; >0 = stop after this many iterations */
+} wm_gen_params;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int wm_create(const wm_config* cfg, int device, wm_handle** out);
+int wm_destroy(wm_handle* h);
+const char* wm_strerror(int status);
+const char* wm_last_error(wm_handle* h);
+
+/* ---- weights (replaces from_pretrained, model.py:265-291) ----------------------------- */
+/* The packed blob layout is defined by the library; the host packer asks where each engine
+ * tensor lives.  dtype: 0 = fp16, 1 = fp32.  Names are listed by wm_tensor_name(0..count-1). */
+int wm_tensor_count(wm_handle* h);
+const char* wm_tensor_name(wm_handle* h, int index);
+int wm_tensor_info(wm_handle* h, const char* name, size_t* offset, size_t* nbytes, int32_t* dtype);
+size_t wm_weights_nbytes(wm_handle* h);
+/* Copy a packed host blob to the device (the handle allocates and owns the device copy). */
+int wm_load_weights(wm_handle* h, const void* host_blob, size_t nbytes);
+/* Use a caller-owned DEVICE blob (e.g. one filled by an NCCL broadcast); not freed by the handle. */
+int wm_adopt_weights(wm_handle* h, void* device_blob, size_t nbytes);
+
+/* ---- logits processors (model.py:1168-1207; HF logits_process.py:1893-1901,1847-1862) -- */
+int wm_set_suppress(wm_handle* h, const int32_t* suppress_ids, int32_t n_suppress,
+                    const int32_t* begin_suppress_ids, int32_t n_begin);
+
+/* ---- frontend + encoder (HF feature_extraction_whisper.py:135-164; modeling_whisper.py:593-647;
+ *      cross-attention K/V projection :325-336) ------------------------------------------- */
+/* f32 PCM @16 kHz on the host, any length (zero-padded / truncated to 480000 samples). */
+int wm_encode_pcm(wm_handle* h, const float* pcm, int32_t n_samples);
+/* f32 log-mel [n_mels][3000] on the host (what WhisperProcessor produces). */
+int wm_encode_mel(wm_handle* h, const float* mel);
+
+/* ---- the speculative decode loop (model.py:404-835 + medusa_utils.py:424-671) ---------- */
+/* prompt: decoder_input_ids.  out_ids receives the FULL sequence (prompt + generated, after
+ * the post-EOS fill of model.py:798-810); capacity must be >= max_length + medusa_num_heads + 2.
+ * accept_lens (capacity >= max_length, may be NULL) receives the per-iteration accept length. */
+int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt, const wm_gen_params* gp,
+                int32_t* out_ids, int32_t* n_out, int32_t* accept_lens, int32_t* n_iter);
+
+/* ---- parity taps / measurements --------------------------------------------------------- */
+int wm_get_mel(wm_handle* h, float* out /* [n_mels][3000] */);
+int wm_get_encoder_out(wm_handle* h, float* out /* [max_source_positions][d_model] */);
+/* Raw (pre-processor) logits of the last executed iteration: which = 0 pass A ([K+1][V], rows =
+ * heads at the last position), 1 = pass B ([K+1][V], rows = tree positions). */
+int wm_last_logits(wm_handle* h, int32_t which, float* out);
+/* Device time (CUDA events on the handle's stream) of the last call: 0 = mel, 1 = encoder
+ * (+cross K/V), 2 = decode loop.  Milliseconds. */
+double wm_last_ms(wm_handle* h, int32_t what);
+/* Number of kernel launches issued by the last wm_encode_* (what=1) / wm_generate (what=2). */
+int64_t wm_last_launches(wm_handle* h, int32_t what);
+/* Decode execution mode: 0 = one graph launch per pass (stage kernels), 1 = persistent
+ * cooperative kernel per speculative iteration.  Returns the previous mode. */
+int wm_set_decode_mode(wm_handle* h, int32_t mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WHISPER_MEDUSA_B200_H_ */

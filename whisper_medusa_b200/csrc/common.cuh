@@ -1,0 +1,151 @@
+// Shared device helpers and engine-internal types (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define WM_HEAD_DIM 64
+#define WM_MAX_T 16          // max query rows of one decode pass (K+1 <= 16)
+#define WM_MAX_DEC_LAYERS 40
+#define WM_MAX_POS 512       // self-KV rows allocated per layer (448 + tree slack)
+#define WM_CROSS_CHUNKS 8    // cross-attention key chunks per head (flash-decoding split)
+#define WM_DEC_THREADS 512   // threads per CTA of the decode GEMM stages (16 warps)
+
+namespace wm {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  // HF ACT2FN["gelu"] = exact erf GELU
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+// D(16x8,f32) += A(16x16,f16,row) * B(16x8,f16,col)
+__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* smem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(s));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                                                  const void* smem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(s));
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------------------
+// decode-side model description (lives in device memory; kernels take a pointer to it)
+// ---------------------------------------------------------------------------------------
+struct DecLayer {
+  const float *ln1_g, *ln1_b;
+  const __half* qkv_w;  // [3d, d]   (q rows pre-scaled by head_dim^-0.5)
+  const float* qkv_b;   // [3d]      (k part zero)
+  const __half* o_w;    // [d, d]
+  const float* o_b;
+  const float *ln2_g, *ln2_b;
+  const __half* cq_w;   // [d, d]    (pre-scaled)
+  const float* cq_b;
+  const __half* co_w;   // [d, d]
+  const float* co_b;
+  const float *ln3_g, *ln3_b;
+  const __half* fc1_w;  // [ffn, d]
+  const float* fc1_b;
+  const __half* fc2_w;  // [d, ffn]
+  const float* fc2_b;
+  __half* self_k;        // [WM_MAX_POS, d]
+  __half* self_v;        // [WM_MAX_POS, d]
+  const __half* cross_kv;  // [S_pad, 2d]  (k | v), written by the encoder-side GEMM
+};
+
+// Loop state of one stream (device memory; the host only reads it back at sync points).
+struct DecState {
+  int L;            // len(input_ids)
+  int kv_len;       // cached self-attention positions before pass A
+  int done;         // loop finished (EOS / max_length / max_iters)
+  int n_iter;       // iterations executed
+  int max_iters;    // 0 = unlimited
+  int max_length;
+  int eos, pad;
+  int begin_index;
+  int accept_last;
+  float temperature, post_thr, post_alpha;
+  int ids[WM_MAX_POS + 32];
+  int cand[WM_MAX_T];            // candidate chain of the current iteration (c0, head 1..K)
+  int accept_hist[WM_MAX_POS];
+  // per-row statistics written by the logits scan, consumed by the accept step
+  int row_argmax[WM_MAX_T];
+  float row_pc[WM_MAX_T];        // softmax prob of the candidate following the row
+  float row_thr[WM_MAX_T];
+};
+
+struct DecModel {
+  int d, H, ffn, V, S, S_pad;
+  int n_layers;      // decoder layers (without the medusa block)
+  int has_block;     // 1 => layers[n_layers] is the medusa block
+  int K;             // medusa heads
+  DecLayer layers[WM_MAX_DEC_LAYERS];
+  const __half* embed;   // [V, d] (also proj_out)
+  const float* pos;      // [max_target_positions, d]
+  const float *lnf_g, *lnf_b;
+  const __half* heads_w; // [(K+1) or K][d, d]
+  const float* heads_b;
+  const uint8_t* tok_mask;  // [V]: bit0 suppress, bit1 begin-suppress
+  const float* pen_tab;     // [WM_MAX_POS + 32]: (factor^(L-start) - 1) as f32, 0 when inactive
+  // activations (fp32)
+  float* x;        // [WM_MAX_T, d] residual stream
+  float* q;        // [WM_MAX_T, d]
+  float* attn;     // [WM_MAX_T, d]
+  float* ffn_h;    // [WM_MAX_T, ffn]
+  float* hidden;   // [WM_MAX_T, d]  final-LN output (block type: input of the block)
+  float* head_h;   // [WM_MAX_T, d]
+  float* cross_part;  // [H][WM_CROSS_CHUNKS][WM_MAX_T][WM_HEAD_DIM + 2]
+  float* logits_a;    // [WM_MAX_T, V]
+  float* logits_b;    // [WM_MAX_T, V]
+  DecState* st;
+  unsigned int* bar;  // grid-barrier words for the persistent kernel
+};
+
+}  // namespace wm

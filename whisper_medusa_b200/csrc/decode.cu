@@ -1,0 +1,920 @@
+// Decode-side kernels of the Medusa speculative loop (sm_100a).
+//
+// One speculative iteration = pass A (the not-yet-cached token(s), all K+1 heads) followed by
+// pass B (verify: the K+1 candidate tokens, base head only) -- reference model.py:635-793 and
+// SURVEY.md 3.3.  Every pass is a chain of "stages"; a stage is a __device__ function written
+// for an arbitrary (cta, n_cta) so that the same code runs either as its own kernel launch
+// (mode 0: one CUDA graph per pass) or inside the persistent cooperative kernel (mode 1: one
+// launch per iteration, grid barriers between stages).
+//
+// Numerics: fp16 weights, fp16 self/cross K/V caches, fp32 activations and accumulation.  The
+// skinny GEMMs (T <= 16 rows) run on mma.sync m16n8k16 with the fp32 activation split into
+// fp16 hi + lo parts (two MMAs), which keeps ~22 mantissa bits of the activation; the path is
+// HBM-bound (weights are streamed exactly once per pass), not tensor-bound.
+#include "common.cuh"
+#include "engine.h"
+
+namespace wm {
+
+// -----------------------------------------------------------------------------------------
+// pass geometry (uniform across the grid; read from the loop state)
+// -----------------------------------------------------------------------------------------
+struct PassGeom {
+  int T;     // query rows of this pass
+  int base;  // position of row 0 (also the self-KV row it writes)
+};
+__device__ __forceinline__ PassGeom pass_geom(const DecModel* m, int mode) {
+  const DecState* st = m->st;
+  PassGeom g;
+  if (mode == 0) {
+    g.T = st->L - st->kv_len;
+    g.base = st->kv_len;
+  } else {
+    g.T = m->K + 1;
+    g.base = st->L;
+  }
+  return g;
+}
+
+// -----------------------------------------------------------------------------------------
+// stage: token + position embedding  (HF modeling_whisper.py:737-763)
+// -----------------------------------------------------------------------------------------
+__device__ void stage_embed(const DecModel* m, int mode, int cta, int ncta) {
+  PassGeom g = pass_geom(m, mode);
+  const DecState* st = m->st;
+  const int d = m->d;
+  for (int t = cta; t < g.T; t += ncta) {
+    int tok = (mode == 0) ? st->ids[g.base + t] : st->cand[t];
+    const __half* e = m->embed + (size_t)tok * d;
+    const float* p = m->pos + (size_t)(g.base + t) * d;
+    float* x = m->x + (size_t)t * d;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) x[j] = __half2float(e[j]) + p[j];
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// skinny GEMM  y[t, n] = sum_k X[t, k] * W[n, k]   (t < 16 rows, W fp16 [N, K] row-major)
+// -----------------------------------------------------------------------------------------
+enum XSrc { XS_LN = 0, XS_PLAIN = 1 };
+enum Epi { EPI_QKV = 0, EPI_RESID, EPI_STORE, EPI_GELU, EPI_HEADS_A, EPI_HEAD_B, EPI_LOGITS };
+
+struct GemmDesc {
+  const __half* W;
+  const float* bias;   // may be null
+  int N, K;
+  // X source
+  int xsrc;            // XSrc
+  const float* X;      // [rows, K] fp32 (for XS_LN: the residual stream)
+  int x_row0;          // first source row
+  int x_rows;          // number of valid rows (<= 16)
+  const float *ln_g, *ln_b;
+  // epilogue
+  int epi;
+  float* out;          // EPI_STORE/GELU/LOGITS/HEAD*: destination [16, ldo]; EPI_RESID: residual stream
+  int ldo;
+  int out_row0;        // EPI_HEADS_A: first destination row
+  __half *kc, *vc;     // EPI_QKV: self K/V cache rows
+  int base;            // EPI_QKV: cache row of token 0
+  int d;               // model dim (EPI_QKV / EPI_HEADS_A)
+};
+
+#define WM_XPAD 32  // halfs of padding per smem activation row => row stride = 64 B (mod 128 B): conflict-free LDS.128
+#define WM_MAXR 3   // max (unit, k-slice) items per warp
+
+// K is processed in `nph` phases of KPH columns so the fp16 hi/lo activation slice fits in
+// shared memory; KPH must be a multiple of 64 (bank-conflict-free row stride, 32-wide chunks).
+__host__ __device__ inline int gemm_nphase(int K) {
+  int nph = (K + 2047) / 2048;
+  while (K % (nph * 64) != 0) ++nph;
+  return nph;
+}
+
+// dynamic shared memory layout of a GEMM stage
+//   xhi [16][KPH + 32] half | xlo [16][KPH + 32] half | partial [items][256] float
+__host__ __device__ inline size_t gemm_smem_bytes(int K) {
+  int nph = gemm_nphase(K);
+  int kph = K / nph;
+  return (size_t)2 * 16 * (kph + WM_XPAD) * sizeof(__half) + (size_t)(2 * 16 + 8) * 256 * sizeof(float);
+}
+
+__device__ __forceinline__ void gemm_epilogue(const GemmDesc& g, int token, int row, float v,
+                                              const __half* xhi, const __half* xlo, int xstride) {
+  if (g.bias) v += g.bias[row];
+  switch (g.epi) {
+    case EPI_QKV: {
+      int d = g.d;
+      if (row < d) {
+        g.out[(size_t)token * g.ldo + row] = v;
+      } else if (row < 2 * d) {
+        g.kc[(size_t)(g.base + token) * d + (row - d)] = __float2half_rn(v);
+      } else {
+        g.vc[(size_t)(g.base + token) * d + (row - 2 * d)] = __float2half_rn(v);
+      }
+      break;
+    }
+    case EPI_RESID:
+      g.out[(size_t)token * g.ldo + row] += v;
+      break;
+    case EPI_STORE:
+    case EPI_LOGITS:
+      g.out[(size_t)token * g.ldo + row] = v;
+      break;
+    case EPI_GELU:
+      g.out[(size_t)token * g.ldo + row] = gelu_erf(v);
+      break;
+    case EPI_HEADS_A: {
+      // stacked heads applied to ONE input row: row = head * d + n  (reference model.py:1274-1280)
+      int head = row / g.d, n = row - head * g.d;
+      float xv = __half2float(xhi[n]) + __half2float(xlo[n]);
+      g.out[(size_t)(g.out_row0 + head) * g.ldo + n] = xv + silu(v);
+      break;
+    }
+    case EPI_HEAD_B: {
+      float xv = __half2float(xhi[(size_t)token * xstride + row]) + __half2float(xlo[(size_t)token * xstride + row]);
+      g.out[(size_t)token * g.ldo + row] = xv + silu(v);
+      break;
+    }
+  }
+}
+
+__device__ void stage_gemm(const GemmDesc& g, int cta, int ncta, unsigned char* smem_raw) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int K = g.K, N = g.N;
+  const int nph = gemm_nphase(K);
+  const int KPH = K / nph;
+  const int xstride = KPH + WM_XPAD;
+  __half* xhi = reinterpret_cast<__half*>(smem_raw);
+  __half* xlo = xhi + 16 * xstride;
+  float* partial = reinterpret_cast<float*>(xlo + 16 * xstride);
+
+  // balanced contiguous row range of this CTA
+  const int rows_per = N / ncta, rem = N % ncta;
+  const int n_begin = cta * rows_per + min(cta, rem);
+  const int n_rows = rows_per + (cta < rem ? 1 : 0);
+  const int n_end = n_begin + n_rows;
+  const int units = (n_rows + 15) >> 4;
+  int ksplit = 1;
+  while (ksplit < 8 && units * ksplit * 2 <= nwarps && ((KPH / (ksplit * 2)) % 32) == 0) ksplit <<= 1;
+  const int items = units * ksplit;   // host guarantees items <= WM_MAXR * nwarps and <= 40
+  const int KS = KPH / ksplit;
+  const int T = g.x_rows;
+
+  float acc[WM_MAXR][8];
+#pragma unroll
+  for (int r = 0; r < WM_MAXR; ++r)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
+
+  for (int ph = 0; ph < nph; ++ph) {
+    // ---- stage the activation slice as fp16 hi/lo ----
+    if (ph > 0) __syncthreads();
+    if (g.xsrc == XS_LN) {
+      // LayerNorm over the full row (nph == 1 for LN stages: K = d <= 2048)
+      for (int r = warp; r < 16; r += nwarps) {
+        __half* hi = xhi + r * xstride;
+        __half* lo = xlo + r * xstride;
+        if (r < T) {
+          const float* x = g.X + (size_t)(g.x_row0 + r) * K;
+          float s = 0.f;
+          for (int j = lane; j < K; j += 32) s += x[j];
+          float mean = warp_sum(s) / (float)K;
+          float v = 0.f;
+          for (int j = lane; j < K; j += 32) { float dlt = x[j] - mean; v += dlt * dlt; }
+          float rstd = rsqrtf(warp_sum(v) / (float)K + 1e-5f);
+          for (int j = lane; j < K; j += 32) {
+            float y = (x[j] - mean) * rstd * g.ln_g[j] + g.ln_b[j];
+            __half h = __float2half_rn(y);
+            hi[j] = h;
+            lo[j] = __float2half_rn(y - __half2float(h));
+          }
+        } else {
+          for (int j = lane; j < K; j += 32) { hi[j] = __float2half_rn(0.f); lo[j] = __float2half_rn(0.f); }
+        }
+      }
+    } else {
+      for (int idx = tid; idx < 16 * KPH; idx += blockDim.x) {
+        int r = idx / KPH, j = idx - r * KPH;
+        float y = (r < T) ? g.X[(size_t)(g.x_row0 + r) * K + ph * KPH + j] : 0.f;
+        __half h = __float2half_rn(y);
+        xhi[r * xstride + j] = h;
+        xlo[r * xstride + j] = __float2half_rn(y - __half2float(h));
+      }
+    }
+    __syncthreads();
+
+    // ---- stream the weights ----
+#pragma unroll
+    for (int r = 0; r < WM_MAXR; ++r) {
+      const int item = warp + r * nwarps;
+      if (item < items) {
+        const int u = item / ksplit, ks = item - u * ksplit;
+        const int row0 = n_begin + u * 16 + gq, row1 = row0 + 8;
+        const bool v0 = row0 < n_end, v1 = row1 < n_end;
+        const __half* w0p = g.W + (size_t)(v0 ? row0 : n_begin) * K + (size_t)ph * KPH + 8 * tq;
+        const __half* w1p = g.W + (size_t)(v1 ? row1 : n_begin) * K + (size_t)ph * KPH + 8 * tq;
+        const __half* xh0 = xhi + gq * xstride + 8 * tq;
+        const __half* xh1 = xhi + (gq + 8) * xstride + 8 * tq;
+        const __half* xl0 = xlo + gq * xstride + 8 * tq;
+        const __half* xl1 = xlo + (gq + 8) * xstride + 8 * tq;
+        const int k0 = ks * KS, k1 = k0 + KS;
+        float* c0 = &acc[r][0];
+        float* c1 = &acc[r][4];
+        for (int k = k0; k < k1; k += 128) {
+          uint4 wa[4], wb[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int kk = k + 32 * c;
+            wa[c] = make_uint4(0, 0, 0, 0);
+            wb[c] = make_uint4(0, 0, 0, 0);
+            if (kk < k1) {
+              if (v0) wa[c] = ldg_nc_v4(w0p + kk);
+              if (v1) wb[c] = ldg_nc_v4(w1p + kk);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int kk = k + 32 * c;
+            if (kk < k1) {
+              const uint4 ah0 = *reinterpret_cast<const uint4*>(xh0 + kk);
+              const uint4 ah1 = *reinterpret_cast<const uint4*>(xh1 + kk);
+              const uint4 al0 = *reinterpret_cast<const uint4*>(xl0 + kk);
+              const uint4 al1 = *reinterpret_cast<const uint4*>(xl1 + kk);
+              mma_16816(c0, ah0.x, ah1.x, ah0.y, ah1.y, wa[c].x, wa[c].y);
+              mma_16816(c0, ah0.z, ah1.z, ah0.w, ah1.w, wa[c].z, wa[c].w);
+              mma_16816(c0, al0.x, al1.x, al0.y, al1.y, wa[c].x, wa[c].y);
+              mma_16816(c0, al0.z, al1.z, al0.w, al1.w, wa[c].z, wa[c].w);
+              mma_16816(c1, ah0.x, ah1.x, ah0.y, ah1.y, wb[c].x, wb[c].y);
+              mma_16816(c1, ah0.z, ah1.z, ah0.w, ah1.w, wb[c].z, wb[c].w);
+              mma_16816(c1, al0.x, al1.x, al0.y, al1.y, wb[c].x, wb[c].y);
+              mma_16816(c1, al0.z, al1.z, al0.w, al1.w, wb[c].z, wb[c].w);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue ----
+  // accumulator element i of n-tile j: token = gq + (i >= 2 ? 8 : 0), weight row = unit*16 + j*8 + 2*tq + (i & 1)
+  if (ksplit == 1) {
+#pragma unroll
+    for (int r = 0; r < WM_MAXR; ++r) {
+      const int item = warp + r * nwarps;
+      if (item < items) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = e >> 2, i = e & 3;
+          const int token = gq + ((i >= 2) ? 8 : 0);
+          const int row = n_begin + item * 16 + j * 8 + 2 * tq + (i & 1);
+          if (token < T && row < n_end) gemm_epilogue(g, token, row, acc[r][e], xhi, xlo, xstride);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < WM_MAXR; ++r) {
+      const int item = warp + r * nwarps;
+      if (item < items) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) partial[(size_t)item * 256 + e * 32 + lane] = acc[r][e];
+      }
+    }
+    __syncthreads();
+    for (int o = tid; o < units * 256; o += blockDim.x) {
+      const int u = o >> 8, el = o & 255;
+      const int e = el >> 5, ln = el & 31;
+      const int j = e >> 2, i = e & 3;
+      const int token = (ln >> 2) + ((i >= 2) ? 8 : 0);
+      const int row = n_begin + u * 16 + j * 8 + 2 * (ln & 3) + (i & 1);
+      if (token < T && row < n_end) {
+        float s = 0.f;
+        for (int ks = 0; ks < ksplit; ++ks) s += partial[(size_t)(u * ksplit + ks) * 256 + el];
+        gemm_epilogue(g, token, row, s, xhi, xlo, xstride);
+      }
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// stage: causal self-attention over the fp16 cache (HF modeling_whisper.py:284-357, T_q <= 16)
+// item = (head, query row); keys 0 .. base + t
+// -----------------------------------------------------------------------------------------
+__device__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw) {
+  PassGeom g = pass_geom(m, mode);
+  const int d = m->d, H = m->H;
+  const DecLayer& L = m->layers[layer];
+  float* s_q = reinterpret_cast<float*>(smem_raw);            // [64]
+  float* s_p = s_q + 64;                                      // [WM_MAX_POS]
+  float* s_red = s_p + WM_MAX_POS;                            // [64]
+  float* s_acc = s_red + 64;                                  // [64 groups][64]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int item = cta; item < H * g.T; item += ncta) {
+    const int h = item / g.T, t = item - h * g.T;
+    const int nk = g.base + t + 1;
+    __syncthreads();
+    if (tid < 64) s_q[tid] = m->q[(size_t)t * d + h * 64 + tid];
+    __syncthreads();
+    // scores
+    float lmax = -INFINITY;
+    for (int j = tid; j < nk; j += blockDim.x) {
+      const uint4* kp = reinterpret_cast<const uint4*>(L.self_k + (size_t)j * d + h * 64);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 kv = kp[c];
+        const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __half22float2(k2[e]);
+          s = fmaf(s_q[c * 8 + 2 * e], f.x, s);
+          s = fmaf(s_q[c * 8 + 2 * e + 1], f.y, s);
+        }
+      }
+      s_p[j] = s;
+      lmax = fmaxf(lmax, s);
+    }
+    lmax = warp_max(lmax);
+    if (lane == 0) s_red[warp] = lmax;
+    __syncthreads();
+    float gmax = -INFINITY;
+    for (int w = 0; w < nwarps; ++w) gmax = fmaxf(gmax, s_red[w]);
+    __syncthreads();
+    float lsum = 0.f;
+    for (int j = tid; j < nk; j += blockDim.x) {
+      float p = expf(s_p[j] - gmax);
+      s_p[j] = p;
+      lsum += p;
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0) s_red[32 + warp] = lsum;
+    __syncthreads();
+    float gsum = 0.f;
+    for (int w = 0; w < nwarps; ++w) gsum += s_red[32 + w];
+    // P * V : thread = (key group kg, dim group dg of 8 dims)
+    const int dg = tid & 7, kg = tid >> 3, ngroups = blockDim.x >> 3;
+    float a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = 0.f;
+    for (int j = kg; j < nk; j += ngroups) {
+      uint4 vv = *reinterpret_cast<const uint4*>(L.self_v + (size_t)j * d + h * 64 + dg * 8);
+      const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+      const float p = s_p[j];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(v2[e]);
+        a[2 * e] = fmaf(p, f.x, a[2 * e]);
+        a[2 * e + 1] = fmaf(p, f.y, a[2 * e + 1]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_acc[kg * 64 + dg * 8 + e] = a[e];
+    __syncthreads();
+    if (tid < 64) {
+      float o = 0.f;
+      for (int gI = 0; gI < ngroups; ++gI) o += s_acc[gI * 64 + tid];
+      m->attn[(size_t)t * d + h * 64 + tid] = o / gsum;
+    }
+  }
+}
+__host__ __device__ inline size_t self_attn_smem_bytes() {
+  return (size_t)(64 + WM_MAX_POS + 64 + 64 * 64) * sizeof(float);
+}
+
+// -----------------------------------------------------------------------------------------
+// stage: cross-attention partials over one key chunk (flash-decoding split over WM_CROSS_CHUNKS)
+// item = (head, chunk); all T query rows at once.  K/V rows: cross_kv[pos][0:d | d:2d].
+// -----------------------------------------------------------------------------------------
+#define WM_CH_MAX 192
+__host__ __device__ inline size_t cross_attn_smem_bytes() {
+  return (size_t)WM_CH_MAX * 72 * sizeof(__half) + (size_t)WM_CH_MAX * 64 * sizeof(__half) +
+         (size_t)WM_MAX_T * WM_CH_MAX * sizeof(float) + (size_t)WM_MAX_T * 64 * sizeof(float) +
+         (size_t)2 * WM_MAX_T * sizeof(float);
+}
+__device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw) {
+  PassGeom g = pass_geom(m, mode);
+  const int d = m->d, H = m->H, S = m->S;
+  const DecLayer& L = m->layers[layer];
+  const int CH = (S + WM_CROSS_CHUNKS - 1) / WM_CROSS_CHUNKS;
+  __half* sK = reinterpret_cast<__half*>(smem_raw);                 // [CH][72]
+  __half* sV = sK + WM_CH_MAX * 72;                                 // [CH][64]
+  float* sS = reinterpret_cast<float*>(sV + WM_CH_MAX * 64);        // [16][WM_CH_MAX]
+  float* sQ = sS + WM_MAX_T * WM_CH_MAX;                            // [16][64]
+  float* sM = sQ + WM_MAX_T * 64;                                   // [16] max, [16] sum
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int T = g.T;
+  for (int item = cta; item < H * WM_CROSS_CHUNKS; item += ncta) {
+    const int h = item / WM_CROSS_CHUNKS, c = item - h * WM_CROSS_CHUNKS;
+    const int j0 = c * CH, nk = max(0, min(S, j0 + CH) - j0);
+    __syncthreads();
+    for (int idx = tid; idx < nk * 8; idx += blockDim.x) {
+      int j = idx >> 3, part = idx & 7;
+      const __half* src = L.cross_kv + (size_t)(j0 + j) * 2 * d + h * 64 + part * 8;
+      *reinterpret_cast<uint4*>(sK + j * 72 + part * 8) = ldg_nc_v4(src);
+      *reinterpret_cast<uint4*>(sV + j * 64 + part * 8) = ldg_nc_v4(src + d);
+    }
+    for (int idx = tid; idx < T * 64; idx += blockDim.x) {
+      int t = idx >> 6, e = idx & 63;
+      sQ[idx] = m->q[(size_t)t * d + h * 64 + e];
+    }
+    __syncthreads();
+    // scores for all (t, j)
+    for (int idx = tid; idx < T * nk; idx += blockDim.x) {
+      int t = idx / nk, j = idx - t * nk;
+      const float* q = sQ + t * 64;
+      const uint4* kp = reinterpret_cast<const uint4*>(sK + j * 72);
+      float s = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        uint4 kv = kp[cc];
+        const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __half22float2(k2[e]);
+          s = fmaf(q[cc * 8 + 2 * e], f.x, s);
+          s = fmaf(q[cc * 8 + 2 * e + 1], f.y, s);
+        }
+      }
+      sS[t * WM_CH_MAX + j] = s;
+    }
+    __syncthreads();
+    // per-row max / exp / sum : warp per row
+    for (int t = warp; t < T; t += nwarps) {
+      float mx = -INFINITY;
+      for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, sS[t * WM_CH_MAX + j]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j < nk; j += 32) {
+        float p = expf(sS[t * WM_CH_MAX + j] - mx);
+        sS[t * WM_CH_MAX + j] = p;
+        sum += p;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) { sM[t] = mx; sM[WM_MAX_T + t] = sum; }
+    }
+    __syncthreads();
+    // P * V : warp per row t; lane = (kg of 4, dg of 8)
+    for (int t = warp; t < T; t += nwarps) {
+      const int dg = lane & 7, kg = lane >> 3;
+      float a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = 0.f;
+      for (int j = kg; j < nk; j += 4) {
+        uint4 vv = *reinterpret_cast<const uint4*>(sV + j * 64 + dg * 8);
+        const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+        const float p = sS[t * WM_CH_MAX + j];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __half22float2(v2[e]);
+          a[2 * e] = fmaf(p, f.x, a[2 * e]);
+          a[2 * e + 1] = fmaf(p, f.y, a[2 * e + 1]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 8);
+        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 16);
+      }
+      float* out = m->cross_part + ((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + t) * (WM_HEAD_DIM + 2);
+      if (kg == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out[dg * 8 + e] = a[e];
+      }
+      if (lane == 0) { out[64] = sM[t]; out[65] = sM[WM_MAX_T + t]; }
+    }
+  }
+}
+
+// stage: combine the chunk partials (fixed order => deterministic)
+__device__ void stage_cross_combine(const DecModel* m, int mode, int cta, int ncta) {
+  PassGeom g = pass_geom(m, mode);
+  const int d = m->d;
+  const int total = g.T * d;
+  for (int idx = cta * blockDim.x + threadIdx.x; idx < total; idx += ncta * blockDim.x) {
+    const int t = idx / d, n = idx - t * d;
+    const int h = n >> 6, e = n & 63;
+    const float* base = m->cross_part + ((size_t)h * WM_CROSS_CHUNKS * WM_MAX_T + t) * (WM_HEAD_DIM + 2);
+    const size_t cstride = (size_t)WM_MAX_T * (WM_HEAD_DIM + 2);
+    float M = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < WM_CROSS_CHUNKS; ++c) M = fmaxf(M, base[c * cstride + 64]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int c = 0; c < WM_CROSS_CHUNKS; ++c) {
+      const float w = expf(base[c * cstride + 64] - M);
+      num = fmaf(w, base[c * cstride + e], num);
+      den = fmaf(w, base[c * cstride + 65], den);
+    }
+    m->attn[(size_t)t * d + n] = num / den;
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// stage: final LayerNorm -> hidden  (HF modeling_whisper.py:791); block type also seeds the block
+// -----------------------------------------------------------------------------------------
+__device__ void stage_final_ln(const DecModel* m, int mode, int cta, int ncta) {
+  PassGeom g = pass_geom(m, mode);
+  const int d = m->d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int t = cta * nwarps + warp; t < g.T; t += ncta * nwarps) {
+    const float* x = m->x + (size_t)t * d;
+    float s = 0.f;
+    for (int j = lane; j < d; j += 32) s += x[j];
+    const float mean = warp_sum(s) / (float)d;
+    float v = 0.f;
+    for (int j = lane; j < d; j += 32) { float dl = x[j] - mean; v += dl * dl; }
+    const float rstd = rsqrtf(warp_sum(v) / (float)d + 1e-5f);
+    float* hid = m->hidden + (size_t)t * d;
+    for (int j = lane; j < d; j += 32) {
+      const float y = (x[j] - mean) * rstd * m->lnf_g[j] + m->lnf_b[j];
+      hid[j] = y;
+      if (m->has_block) {
+        // medusa_block consumes last_hidden_state (reference model.py:1374-1376); base logits use it
+        // directly (model.py:1287).  Pass A: only the last row feeds vocab row 0; pass B: every row.
+        if (mode == 1) m->head_h[(size_t)t * d + j] = y;
+        else if (t == g.T - 1) m->head_h[j] = y;
+      }
+    }
+  }
+}
+// block type: residual stream of the extra layer starts from the LayerNorm'ed hidden states
+__device__ void stage_copy_hidden_to_x(const DecModel* m, int mode, int cta, int ncta) {
+  PassGeom g = pass_geom(m, mode);
+  const int total = g.T * m->d;
+  for (int idx = cta * blockDim.x + threadIdx.x; idx < total; idx += ncta * blockDim.x) m->x[idx] = m->hidden[idx];
+}
+
+// -----------------------------------------------------------------------------------------
+// stage: logits scan = logits processors + argmax (+ softmax statistics for typical acceptance)
+//   processors: HF logits_process.py:1893-1901 (suppress), :1847-1862 (begin), :1742-1772 (EOS decay)
+//   pass A: generate_candidates with top-1 per head (medusa_utils.py:446-457)
+//   pass B: evaluate_posterior (medusa_utils.py:547-588)
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ float processed_logit(const float* row, int j, const uint8_t* mask, bool begin_on,
+                                                 int eos, float pen) {
+  const uint8_t mk = mask[j];
+  if ((mk & 1) || (begin_on && (mk & 2))) return -INFINITY;
+  float v = row[j];
+  if (j == eos && pen != 0.f) v = v + fabsf(v) * pen;
+  return v;
+}
+
+__device__ void block_argmax(float& v, int& i, float* s_val, int* s_idx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { s_val[warp] = v; s_idx[warp] = i; }
+  __syncthreads();
+  v = s_val[0]; i = s_idx[0];
+  for (int w = 1; w < nwarps; ++w) {
+    float ov = s_val[w]; int oi = s_idx[w];
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+__device__ float block_sum(float v, float* s_val) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) s_val[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int w = 0; w < nwarps; ++w) s += s_val[w];
+  return s;
+}
+
+__device__ void stage_select(const DecModel* m, int mode, int cta, int ncta, unsigned char* smem_raw) {
+  DecState* st = m->st;
+  const int V = m->V, K = m->K;
+  float* s_val = reinterpret_cast<float*>(smem_raw);
+  int* s_idx = reinterpret_cast<int*>(s_val + 32);
+  const int L = st->L;
+  const bool begin_on = (L == st->begin_index);
+  const float pen = m->pen_tab[L];
+  const int eos = st->eos;
+  const float* logits = (mode == 0) ? m->logits_a : m->logits_b;
+  for (int r = cta; r <= K; r += ncta) {
+    const float* row = logits + (size_t)r * V;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+      float v = processed_logit(row, j, m->tok_mask, begin_on, eos, pen);
+      if (v > bv) { bv = v; bi = j; }   // ascending j per thread => first maximum kept
+    }
+    if (bi == 0x7fffffff) bi = threadIdx.x < V ? threadIdx.x : 0;
+    block_argmax(bv, bi, s_val, s_idx);
+    if (mode == 0) {
+      if (threadIdx.x == 0) st->cand[r] = bi;
+      continue;
+    }
+    if (threadIdx.x == 0) st->row_argmax[r] = bi;
+    if (r >= K) continue;   // evaluate_posterior reads logits[:, :-1]
+    const float temp = st->temperature;
+    if (temp == 0.f) continue;
+    const float inv_t = 1.0f / temp;
+    const float mx = bv * inv_t;   // max of the temperature-scaled row (temp > 0)
+    float z = 0.f;
+    for (int j = threadIdx.x; j < V; j += blockDim.x)
+      z += expf(processed_logit(row, j, m->tok_mask, begin_on, eos, pen) * inv_t - mx);
+    z = block_sum(z, s_val);
+    float ent = 0.f;
+    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+      float p = expf(processed_logit(row, j, m->tok_mask, begin_on, eos, pen) * inv_t - mx) / z;
+      ent += p * logf(p + 1e-5f);
+    }
+    ent = -block_sum(ent, s_val);
+    if (threadIdx.x == 0) {
+      const int c = st->cand[r + 1];
+      const float pc = expf(processed_logit(row, c, m->tok_mask, begin_on, eos, pen) * inv_t - mx) / z;
+      st->row_pc[r] = pc;
+      st->row_thr[r] = fminf(st->post_thr, expf(-ent) * st->post_alpha);
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// stage: accept + bookkeeping (single thread)
+//   evaluate_posterior (chain => one candidate), update_inference_inputs (medusa_utils.py:630-652),
+//   KV trim (model.py:383-401: chain rows are contiguous => kv_len is just advanced), stop rules
+//   (model.py:774-793).
+// -----------------------------------------------------------------------------------------
+__device__ void stage_accept(const DecModel* m) {
+  DecState* st = m->st;
+  const int K = m->K;
+  const int L = st->L;
+  int a = 0;
+  if (st->temperature == 0.f) {
+    while (a < K && st->cand[a + 1] == st->row_argmax[a]) ++a;
+  } else {
+    while (a < K && st->row_pc[a] > st->row_thr[a]) ++a;
+  }
+  int n_new = a + 1;
+  for (int i = 0; i <= a; ++i) st->ids[L + i] = st->cand[i];
+  if (a == 0) { st->ids[L + 1] = st->row_argmax[0]; n_new = 2; }
+  bool eos = false;
+  for (int i = 0; i < n_new; ++i) eos |= (st->ids[L + i] == st->eos);
+  const int newL = L + n_new;
+  st->L = newL;
+  st->kv_len = newL - 1;
+  st->accept_last = a;
+  st->accept_hist[st->n_iter] = a;
+  st->n_iter += 1;
+  bool done = eos || newL >= st->max_length || newL + K >= st->max_length;
+  if (st->max_iters > 0 && st->n_iter >= st->max_iters) done = true;
+  if (done) st->done = 1;
+}
+
+// -----------------------------------------------------------------------------------------
+// GEMM descriptors of the stages
+// -----------------------------------------------------------------------------------------
+enum StageId {
+  ST_EMBED = 0, ST_QKV, ST_SELF_ATTN, ST_OPROJ, ST_CROSS_Q, ST_CROSS_ATTN, ST_CROSS_COMBINE, ST_CROSS_O,
+  ST_FC1, ST_FC2, ST_FINAL_LN, ST_COPY_HIDDEN, ST_HEADS, ST_VOCAB, ST_SELECT, ST_ACCEPT
+};
+
+__device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mode, int layer) {
+  PassGeom pg = pass_geom(m, mode);
+  GemmDesc g;
+  const int d = m->d;
+  g.d = d;
+  g.x_row0 = 0;
+  g.x_rows = pg.T;
+  g.base = pg.base;
+  g.out_row0 = 0;
+  g.ln_g = g.ln_b = nullptr;
+  g.kc = g.vc = nullptr;
+  g.bias = nullptr;
+  const DecLayer& L = m->layers[layer];
+  switch (stage) {
+    case ST_QKV:
+      g.W = L.qkv_w; g.bias = L.qkv_b; g.N = 3 * d; g.K = d;
+      g.xsrc = XS_LN; g.X = m->x; g.ln_g = L.ln1_g; g.ln_b = L.ln1_b;
+      g.epi = EPI_QKV; g.out = m->q; g.ldo = d; g.kc = L.self_k; g.vc = L.self_v;
+      break;
+    case ST_OPROJ:
+      g.W = L.o_w; g.bias = L.o_b; g.N = d; g.K = d;
+      g.xsrc = XS_PLAIN; g.X = m->attn;
+      g.epi = EPI_RESID; g.out = m->x; g.ldo = d;
+      break;
+    case ST_CROSS_Q:
+      g.W = L.cq_w; g.bias = L.cq_b; g.N = d; g.K = d;
+      g.xsrc = XS_LN; g.X = m->x; g.ln_g = L.ln2_g; g.ln_b = L.ln2_b;
+      g.epi = EPI_STORE; g.out = m->q; g.ldo = d;
+      break;
+    case ST_CROSS_O:
+      g.W = L.co_w; g.bias = L.co_b; g.N = d; g.K = d;
+      g.xsrc = XS_PLAIN; g.X = m->attn;
+      g.epi = EPI_RESID; g.out = m->x; g.ldo = d;
+      break;
+    case ST_FC1:
+      g.W = L.fc1_w; g.bias = L.fc1_b; g.N = m->ffn; g.K = d;
+      g.xsrc = XS_LN; g.X = m->x; g.ln_g = L.ln3_g; g.ln_b = L.ln3_b;
+      g.epi = EPI_GELU; g.out = m->ffn_h; g.ldo = m->ffn;
+      break;
+    case ST_FC2:
+      g.W = L.fc2_w; g.bias = L.fc2_b; g.N = d; g.K = m->ffn;
+      g.xsrc = XS_PLAIN; g.X = m->ffn_h;
+      g.epi = EPI_RESID; g.out = m->x; g.ldo = d;
+      break;
+    case ST_HEADS:
+      g.bias = m->heads_b; g.W = m->heads_w; g.K = d; g.xsrc = XS_PLAIN; g.out = m->head_h; g.ldo = d;
+      if (mode == 0) {
+        // pass A: every head on the last position (generate_candidates reads logits[:, -1])
+        g.X = m->has_block ? m->x : m->hidden;
+        g.x_row0 = pg.T - 1; g.x_rows = 1;
+        g.N = (m->has_block ? m->K : m->K + 1) * d;
+        g.epi = EPI_HEADS_A; g.out_row0 = m->has_block ? 1 : 0;
+      } else {
+        // pass B (base_head type only): head 0 on every tree position (disable_medusa, model.py:1281-1284)
+        g.X = m->hidden; g.N = d; g.epi = EPI_HEAD_B;
+      }
+      break;
+    case ST_VOCAB:
+    default:
+      g.W = m->embed; g.N = m->V; g.K = d;
+      g.xsrc = XS_PLAIN; g.X = m->head_h; g.x_rows = m->K + 1;
+      g.epi = EPI_LOGITS; g.out = (mode == 0) ? m->logits_a : m->logits_b; g.ldo = m->V;
+      break;
+  }
+  return g;
+}
+
+__device__ void run_stage(const DecModel* m, int stage, int mode, int layer, int cta, int ncta, unsigned char* smem) {
+  switch (stage) {
+    case ST_EMBED: stage_embed(m, mode, cta, ncta); break;
+    case ST_SELF_ATTN: stage_self_attn(m, mode, layer, cta, ncta, smem); break;
+    case ST_CROSS_ATTN: stage_cross_attn(m, mode, layer, cta, ncta, smem); break;
+    case ST_CROSS_COMBINE: stage_cross_combine(m, mode, cta, ncta); break;
+    case ST_FINAL_LN: stage_final_ln(m, mode, cta, ncta); break;
+    case ST_COPY_HIDDEN: stage_copy_hidden_to_x(m, mode, cta, ncta); break;
+    case ST_SELECT: stage_select(m, mode, cta, ncta, smem); break;
+    case ST_ACCEPT: if (cta == 0 && threadIdx.x == 0) stage_accept(m); break;
+    default: {
+      GemmDesc g = make_gemm_desc(m, stage, mode, layer);
+      stage_gemm(g, cta, ncta, smem);
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// mode 0: one kernel per stage (captured into a CUDA graph per pass by the host)
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WM_DEC_THREADS, 1)
+dec_stage_kernel(const DecModel* __restrict__ m, int stage, int mode, int layer) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (m->st->done) return;
+  run_stage(m, stage, mode, layer, blockIdx.x, gridDim.x, smem);
+}
+
+// -----------------------------------------------------------------------------------------
+// mode 1: persistent cooperative kernel -- one launch per speculative iteration
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch, int ncta) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += 1;
+    __threadfence();
+    unsigned int prev = atomicAdd(&bar[0], 1u);
+    if (prev == (unsigned int)ncta * epoch - 1u) {
+      // last arriver releases everybody
+      atomicExch(&bar[1], epoch);
+    } else {
+      volatile unsigned int* flag = &bar[1];
+      while (*flag < epoch) { __nanosleep(20); }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct PassPlan {
+  int n_layers_full;  // layers that run completely
+  int has_block;
+};
+
+__device__ void run_pass(const DecModel* m, int mode, int cta, int ncta, unsigned char* smem, unsigned int& epoch) {
+  unsigned int* bar = m->bar;
+#define WM_STAGE(st, layer)                       \
+  run_stage(m, st, mode, layer, cta, ncta, smem); \
+  grid_barrier(bar, epoch, ncta);
+  WM_STAGE(ST_EMBED, 0)
+  for (int l = 0; l < m->n_layers; ++l) {
+    WM_STAGE(ST_QKV, l)
+    WM_STAGE(ST_SELF_ATTN, l)
+    WM_STAGE(ST_OPROJ, l)
+    WM_STAGE(ST_CROSS_Q, l)
+    WM_STAGE(ST_CROSS_ATTN, l)
+    WM_STAGE(ST_CROSS_COMBINE, l)
+    WM_STAGE(ST_CROSS_O, l)
+    WM_STAGE(ST_FC1, l)
+    WM_STAGE(ST_FC2, l)
+  }
+  WM_STAGE(ST_FINAL_LN, 0)
+  if (m->has_block) {
+    const int l = m->n_layers;
+    WM_STAGE(ST_COPY_HIDDEN, 0)
+    WM_STAGE(ST_QKV, l)
+    if (mode == 0) {
+      WM_STAGE(ST_SELF_ATTN, l)
+      WM_STAGE(ST_OPROJ, l)
+      WM_STAGE(ST_CROSS_Q, l)
+      WM_STAGE(ST_CROSS_ATTN, l)
+      WM_STAGE(ST_CROSS_COMBINE, l)
+      WM_STAGE(ST_CROSS_O, l)
+      WM_STAGE(ST_FC1, l)
+      WM_STAGE(ST_FC2, l)
+      WM_STAGE(ST_HEADS, 0)
+    }
+  } else {
+    WM_STAGE(ST_HEADS, 0)
+  }
+  WM_STAGE(ST_VOCAB, 0)
+  WM_STAGE(ST_SELECT, 0)
+  if (mode == 1) {
+    WM_STAGE(ST_ACCEPT, 0)
+  }
+#undef WM_STAGE
+}
+
+__global__ void __launch_bounds__(WM_DEC_THREADS, 1)
+dec_iteration_kernel(const DecModel* __restrict__ m) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (m->st->done) return;   // uniform: `done` only changes in the last stage of an iteration
+  // bar[0] = arrival counter, bar[1] = released epoch, bar[2] = epoch at kernel entry.  bar[2]
+  // is only rewritten after the last barrier of a launch, i.e. after every CTA has read it.
+  unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(&m->bar[2]);
+  run_pass(m, 0, blockIdx.x, gridDim.x, smem, epoch);
+  run_pass(m, 1, blockIdx.x, gridDim.x, smem, epoch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) m->bar[2] = epoch;
+}
+
+// -----------------------------------------------------------------------------------------
+// host-side launchers
+// -----------------------------------------------------------------------------------------
+size_t dec_smem_bytes(int d, int ffn) {
+  size_t s = gemm_smem_bytes(d);
+  size_t s2 = gemm_smem_bytes(ffn);
+  if (s2 > s) s = s2;
+  if (self_attn_smem_bytes() > s) s = self_attn_smem_bytes();
+  if (cross_attn_smem_bytes() > s) s = cross_attn_smem_bytes();
+  return s;
+}
+
+cudaError_t dec_configure(size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(dec_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dec_iteration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+static int stage_grid(int stage, int T, int n_sm, int H, int K) {
+  switch (stage) {
+    case ST_EMBED: return T;
+    case ST_SELF_ATTN: return H * T;
+    case ST_CROSS_ATTN: return H * WM_CROSS_CHUNKS;
+    case ST_CROSS_COMBINE: return 8;
+    case ST_FINAL_LN: return 1;
+    case ST_COPY_HIDDEN: return 8;
+    case ST_SELECT: return K + 1;
+    case ST_ACCEPT: return 1;
+    default: return n_sm;
+  }
+}
+
+// Enqueue one pass as individual stage kernels (captured into a graph by the caller).
+cudaError_t dec_enqueue_pass(const DecModel* dm, const DecHostInfo& hi, int mode, int T, cudaStream_t s, int64_t* n_launch) {
+  auto launch = [&](int stage, int layer) {
+    int grid = stage_grid(stage, T, hi.n_sm, hi.H, hi.K);
+    dec_stage_kernel<<<grid, WM_DEC_THREADS, hi.smem, s>>>(dm, stage, mode, layer);
+    if (n_launch) ++*n_launch;
+  };
+  launch(ST_EMBED, 0);
+  auto layer_full = [&](int l) {
+    launch(ST_QKV, l); launch(ST_SELF_ATTN, l); launch(ST_OPROJ, l); launch(ST_CROSS_Q, l);
+    launch(ST_CROSS_ATTN, l); launch(ST_CROSS_COMBINE, l); launch(ST_CROSS_O, l); launch(ST_FC1, l); launch(ST_FC2, l);
+  };
+  for (int l = 0; l < hi.n_layers; ++l) layer_full(l);
+  launch(ST_FINAL_LN, 0);
+  if (hi.has_block) {
+    launch(ST_COPY_HIDDEN, 0);
+    if (mode == 0) { layer_full(hi.n_layers); launch(ST_HEADS, 0); }
+    else launch(ST_QKV, hi.n_layers);
+  } else {
+    launch(ST_HEADS, 0);
+  }
+  launch(ST_VOCAB, 0);
+  launch(ST_SELECT, 0);
+  if (mode == 1) launch(ST_ACCEPT, 0);
+  return cudaGetLastError();
+}
+
+cudaError_t dec_launch_iteration(const DecModel* dm, const DecHostInfo& hi, cudaStream_t s) {
+  void* args[] = {(void*)&dm};
+  return cudaLaunchCooperativeKernel((void*)dec_iteration_kernel, dim3(hi.n_sm), dim3(WM_DEC_THREADS), args, hi.smem, s);
+}
+
+}  // namespace wm

@@ -1,0 +1,665 @@
+// C ABI + host orchestration of the Whisper-Medusa decode path (see include/whisper_medusa_b200.h).
+//
+// Host responsibilities only: own device memory, define the packed-weight layout, enqueue the
+// mel / encoder / cross-KV kernels for a clip, and drive the speculative loop (CUDA graphs of
+// stage kernels, or the persistent per-iteration kernel).  No arithmetic of the path runs on
+// the host; there is no CPU fallback.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/whisper_medusa_b200.h"
+#include "common.cuh"
+#include "engine.h"
+
+using namespace wm;
+
+namespace {
+
+struct TensorInfo {
+  std::string name;
+  size_t offset, nbytes;
+  int dtype;  // 0 f16, 1 f32
+};
+
+constexpr int kFrames = 3000;
+constexpr int kSamples = 480000;
+constexpr int kNFreq = 201;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct wm_handle {
+  wm_config cfg;
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // weights
+  std::vector<TensorInfo> tensors;
+  std::map<std::string, int> tindex;
+  size_t wbytes = 0;
+  unsigned char* wdev = nullptr;
+  bool wowned = false, wready = false;
+  // dims
+  int S = 0, S_pad = 0, n_dec = 0;  // n_dec = decoder layers + block
+  // encoder buffers
+  float *pcm = nullptr, *mel32 = nullptr, *melfb = nullptr, *x32 = nullptr, *enc32 = nullptr;
+  __half *x_tm = nullptr, *h1 = nullptr, *ln16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *ffn16 = nullptr,
+         *enc16 = nullptr;
+  int* gmax = nullptr;
+  std::vector<__half*> cross_kv, self_k, self_v;
+  // decode buffers
+  DecModel hm;             // host copy
+  DecModel* dm = nullptr;  // device copy
+  DecState* st = nullptr;
+  uint8_t* tok_mask = nullptr;
+  float* pen_tab = nullptr;
+  unsigned int* bar = nullptr;
+  DecHostInfo hi;
+  std::map<int, cudaGraphExec_t> graph_a;  // keyed by T
+  cudaGraphExec_t graph_b = nullptr;
+  int64_t launches_a[WM_MAX_T + 1] = {0};
+  int64_t launches_b = 0;
+  int decode_mode = 0;
+  bool encoded = false;
+  // pinned staging + timing
+  int* h_state = nullptr;  // pinned copy of the DecState header
+  float* h_stage = nullptr;  // pinned staging for pcm / mel
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double ms[3] = {0, 0, 0};
+  int64_t launches[3] = {0, 0, 0};
+  float last_pen_factor = 0.f;
+  int last_pen_start = -2, last_pen_prompt = -1;
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      char _b[512];                                                                                \
+      snprintf(_b, sizeof _b, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      h->err = _b;                                                                                 \
+      return WM_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+static int fail(wm_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed-weight layout
+// ---------------------------------------------------------------------------------------------
+static void add_tensor(wm_handle* h, const std::string& name, size_t elems, int dtype) {
+  TensorInfo t;
+  t.name = name;
+  t.offset = align_up(h->wbytes, 256);
+  t.nbytes = elems * (dtype == 0 ? 2 : 4);
+  t.dtype = dtype;
+  h->wbytes = t.offset + t.nbytes;
+  h->tindex[name] = (int)h->tensors.size();
+  h->tensors.push_back(t);
+}
+
+static void build_layout(wm_handle* h) {
+  const wm_config& c = h->cfg;
+  const size_t d = c.d_model, f = c.ffn_dim, V = c.vocab_size;
+  add_tensor(h, "enc.conv1_w", d * 256, 0);
+  add_tensor(h, "enc.conv1_b", d, 1);
+  add_tensor(h, "enc.conv2_w", d * 3 * d, 0);
+  add_tensor(h, "enc.conv2_b", d, 1);
+  add_tensor(h, "enc.pos", (size_t)c.max_source_positions * d, 1);
+  for (int i = 0; i < c.enc_layers; ++i) {
+    std::string p = "enc." + std::to_string(i) + ".";
+    add_tensor(h, p + "ln1_g", d, 1); add_tensor(h, p + "ln1_b", d, 1);
+    add_tensor(h, p + "qkv_w", 3 * d * d, 0); add_tensor(h, p + "qkv_b", 3 * d, 1);
+    add_tensor(h, p + "o_w", d * d, 0); add_tensor(h, p + "o_b", d, 1);
+    add_tensor(h, p + "ln2_g", d, 1); add_tensor(h, p + "ln2_b", d, 1);
+    add_tensor(h, p + "fc1_w", f * d, 0); add_tensor(h, p + "fc1_b", f, 1);
+    add_tensor(h, p + "fc2_w", d * f, 0); add_tensor(h, p + "fc2_b", d, 1);
+  }
+  add_tensor(h, "enc.lnf_g", d, 1); add_tensor(h, "enc.lnf_b", d, 1);
+  add_tensor(h, "dec.embed", V * d, 0);
+  add_tensor(h, "dec.pos", (size_t)c.max_target_positions * d, 1);
+  for (int i = 0; i < h->n_dec; ++i) {
+    std::string p = "dec." + std::to_string(i) + ".";
+    add_tensor(h, p + "ln1_g", d, 1); add_tensor(h, p + "ln1_b", d, 1);
+    add_tensor(h, p + "qkv_w", 3 * d * d, 0); add_tensor(h, p + "qkv_b", 3 * d, 1);
+    add_tensor(h, p + "o_w", d * d, 0); add_tensor(h, p + "o_b", d, 1);
+    add_tensor(h, p + "ln2_g", d, 1); add_tensor(h, p + "ln2_b", d, 1);
+    add_tensor(h, p + "cq_w", d * d, 0); add_tensor(h, p + "cq_b", d, 1);
+    add_tensor(h, p + "ckv_w", 2 * d * d, 0); add_tensor(h, p + "ckv_b", 2 * d, 1);
+    add_tensor(h, p + "co_w", d * d, 0); add_tensor(h, p + "co_b", d, 1);
+    add_tensor(h, p + "ln3_g", d, 1); add_tensor(h, p + "ln3_b", d, 1);
+    add_tensor(h, p + "fc1_w", f * d, 0); add_tensor(h, p + "fc1_b", f, 1);
+    add_tensor(h, p + "fc2_w", d * f, 0); add_tensor(h, p + "fc2_b", d, 1);
+  }
+  add_tensor(h, "dec.lnf_g", d, 1); add_tensor(h, "dec.lnf_b", d, 1);
+  const size_t nh = c.medusa_block ? c.medusa_num_heads : c.medusa_num_heads + 1;
+  add_tensor(h, "heads_w", nh * d * d, 0);
+  add_tensor(h, "heads_b", nh * d, 1);
+  h->wbytes = align_up(h->wbytes, 256);
+}
+
+template <typename T>
+static const T* wptr(wm_handle* h, const std::string& name) {
+  auto it = h->tindex.find(name);
+  if (it == h->tindex.end()) return nullptr;
+  return reinterpret_cast<const T*>(h->wdev + h->tensors[it->second].offset);
+}
+
+// ---------------------------------------------------------------------------------------------
+// slaney mel filter bank [201][80]  (HF audio_utils.py mel_filter_bank, norm="slaney",
+// mel_scale="slaney"; called from feature_extraction_whisper.py:95-103)
+// ---------------------------------------------------------------------------------------------
+static double hz_to_mel(double f) {
+  const double min_log_hz = 1000.0, min_log_mel = 15.0, logstep = 27.0 / std::log(6.4);
+  return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) * logstep : 3.0 * f / 200.0;
+}
+static double mel_to_hz(double m) {
+  const double min_log_hz = 1000.0, min_log_mel = 15.0, logstep = std::log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : 200.0 * m / 3.0;
+}
+static std::vector<float> build_mel_filters(int n_mels) {
+  std::vector<double> ff(n_mels + 2);
+  const double m0 = hz_to_mel(0.0), m1 = hz_to_mel(8000.0);
+  for (int i = 0; i < n_mels + 2; ++i) ff[i] = mel_to_hz(m0 + (m1 - m0) * i / (n_mels + 1));
+  std::vector<float> fb((size_t)kNFreq * n_mels);
+  for (int k = 0; k < kNFreq; ++k) {
+    const double fk = 8000.0 * k / (kNFreq - 1);
+    for (int m = 0; m < n_mels; ++m) {
+      const double down = (fk - ff[m]) / (ff[m + 1] - ff[m]);
+      const double up = (ff[m + 2] - fk) / (ff[m + 2] - ff[m + 1]);
+      double v = std::fmax(0.0, std::fmin(down, up));
+      v *= 2.0 / (ff[m + 2] - ff[m]);
+      fb[(size_t)k * n_mels + m] = (float)v;
+    }
+  }
+  return fb;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t dalloc(T** p, size_t elems) {
+  cudaError_t e = cudaMalloc((void**)p, elems * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemset(*p, 0, elems * sizeof(T));
+}
+
+extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
+  if (!cfg || !out) return WM_ERR_INVALID;
+  *out = nullptr;
+  wm_handle* h = new wm_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  const wm_config& c = h->cfg;
+  auto bad = [&](const char* m) { h->err = m; *out = h; return WM_ERR_INVALID; };
+  if (c.d_model % 128 != 0 || c.n_heads * WM_HEAD_DIM != c.d_model) return bad("d_model must be n_heads*64 and a multiple of 128");
+  if (c.ffn_dim % 128 != 0) return bad("ffn_dim must be a multiple of 128");
+  if (c.n_mels != 80) return bad("n_mels must be 80");
+  if (c.medusa_num_heads < 1 || c.medusa_num_heads + 1 > WM_MAX_T) return bad("medusa_num_heads must be in [1, 15]");
+  if (c.dec_layers + 1 > WM_MAX_DEC_LAYERS) return bad("too many decoder layers");
+  if (c.max_target_positions + c.medusa_num_heads + 2 > WM_MAX_POS) return bad("max_target_positions too large");
+  if (c.max_source_positions != 1500) return bad("max_source_positions must be 1500 (30 s window)");
+  *out = h;
+  h->S = c.max_source_positions;
+  h->S_pad = (int)align_up(h->S, 128);
+  h->n_dec = c.dec_layers + (c.medusa_block ? 1 : 0);
+  build_layout(h);
+  if (device < 0) return WM_OK;  // layout-only handle (weight packing / tests on a box without a GPU)
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(h, WM_ERR_UNSUPPORTED, "this engine is built for sm_100a (B200) only");
+  h->n_sm = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CK(cudaEventCreate(&e));
+
+  const size_t d = c.d_model, f = c.ffn_dim, V = c.vocab_size, SP = h->S_pad;
+  CK(dalloc(&h->pcm, (size_t)kSamples));
+  CK(dalloc(&h->mel32, (size_t)80 * kFrames));
+  CK(dalloc(&h->melfb, (size_t)kNFreq * 80));
+  CK(dalloc(&h->gmax, 1));
+  CK(dalloc(&h->x_tm, (size_t)3080 * 80));
+  CK(dalloc(&h->h1, (size_t)3080 * d));
+  CK(dalloc(&h->x32, SP * d));
+  CK(dalloc(&h->enc32, SP * d));
+  CK(dalloc(&h->ln16, SP * d));
+  CK(dalloc(&h->qkv16, SP * 3 * d));
+  CK(dalloc(&h->att16, SP * d));
+  CK(dalloc(&h->ffn16, SP * f));
+  CK(dalloc(&h->enc16, SP * d));
+  h->cross_kv.resize(h->n_dec);
+  h->self_k.resize(h->n_dec);
+  h->self_v.resize(h->n_dec);
+  for (int i = 0; i < h->n_dec; ++i) {
+    CK(dalloc(&h->cross_kv[i], SP * 2 * d));
+    CK(dalloc(&h->self_k[i], (size_t)WM_MAX_POS * d));
+    CK(dalloc(&h->self_v[i], (size_t)WM_MAX_POS * d));
+  }
+  {
+    std::vector<float> fb = build_mel_filters(80);
+    CK(cudaMemcpy(h->melfb, fb.data(), fb.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // decode buffers
+  DecModel& m = h->hm;
+  memset(&m, 0, sizeof m);
+  m.d = (int)d; m.H = c.n_heads; m.ffn = (int)f; m.V = (int)V; m.S = h->S; m.S_pad = h->S_pad;
+  m.n_layers = c.dec_layers; m.has_block = c.medusa_block ? 1 : 0; m.K = c.medusa_num_heads;
+  CK(dalloc(&m.x, (size_t)WM_MAX_T * d));
+  CK(dalloc(&m.q, (size_t)WM_MAX_T * d));
+  CK(dalloc(&m.attn, (size_t)WM_MAX_T * d));
+  CK(dalloc(&m.ffn_h, (size_t)WM_MAX_T * f));
+  CK(dalloc(&m.hidden, (size_t)WM_MAX_T * d));
+  CK(dalloc(&m.head_h, (size_t)WM_MAX_T * d));
+  CK(dalloc(&m.cross_part, (size_t)c.n_heads * WM_CROSS_CHUNKS * WM_MAX_T * (WM_HEAD_DIM + 2)));
+  CK(dalloc(&m.logits_a, (size_t)WM_MAX_T * V));
+  CK(dalloc(&m.logits_b, (size_t)WM_MAX_T * V));
+  CK(dalloc(&h->st, 1));
+  CK(dalloc(&h->tok_mask, V));
+  CK(dalloc(&h->pen_tab, (size_t)WM_MAX_POS + 32));
+  CK(dalloc(&h->bar, 8));
+  CK(dalloc(&h->dm, 1));
+  m.st = h->st; m.tok_mask = h->tok_mask; m.pen_tab = h->pen_tab; m.bar = h->bar;
+  CK(cudaMallocHost((void**)&h->h_state, 64 * sizeof(int)));
+  CK(cudaMallocHost((void**)&h->h_stage, (size_t)kSamples * sizeof(float)));
+
+  h->hi.n_sm = h->n_sm; h->hi.H = c.n_heads; h->hi.K = c.medusa_num_heads; h->hi.n_layers = c.dec_layers;
+  h->hi.has_block = m.has_block;
+  h->hi.smem = dec_smem_bytes((int)d, (int)f);
+  CK(dec_configure(h->hi.smem));
+  CK(enc_gemm_configure());
+  // the skinny-GEMM work split assumes at most WM_MAXR(3) 16-row units per warp
+  {
+    const int rows = (int)((V + h->n_sm - 1) / h->n_sm);
+    if ((rows + 15) / 16 > 3 * (WM_DEC_THREADS / 32)) return fail(h, WM_ERR_UNSUPPORTED, "too few SMs for the vocab projection split");
+  }
+  return WM_OK;
+}
+
+extern "C" int wm_destroy(wm_handle* h) {
+  if (!h) return WM_OK;
+  if (h->device < 0) { delete h; return WM_OK; }
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& kv : h->graph_a) cudaGraphExecDestroy(kv.second);
+  if (h->graph_b) cudaGraphExecDestroy(h->graph_b);
+  auto F = [](void* p) { if (p) cudaFree(p); };
+  F(h->pcm); F(h->mel32); F(h->melfb); F(h->gmax); F(h->x_tm); F(h->h1); F(h->x32); F(h->enc32); F(h->ln16);
+  F(h->qkv16); F(h->att16); F(h->ffn16); F(h->enc16);
+  for (auto p : h->cross_kv) F(p);
+  for (auto p : h->self_k) F(p);
+  for (auto p : h->self_v) F(p);
+  F(h->hm.x); F(h->hm.q); F(h->hm.attn); F(h->hm.ffn_h); F(h->hm.hidden); F(h->hm.head_h); F(h->hm.cross_part);
+  F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->dm);
+  if (h->wowned) F(h->wdev);
+  if (h->h_state) cudaFreeHost(h->h_state);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return WM_OK;
+}
+
+extern "C" const char* wm_strerror(int status) {
+  switch (status) {
+    case WM_OK: return "ok";
+    case WM_ERR_INVALID: return "invalid argument or configuration";
+    case WM_ERR_CUDA: return "CUDA error";
+    case WM_ERR_STATE: return "call order violated";
+    case WM_ERR_UNSUPPORTED: return "not supported";
+    case WM_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+  }
+}
+extern "C" const char* wm_last_error(wm_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+// ---------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------
+extern "C" int wm_tensor_count(wm_handle* h) { return h ? (int)h->tensors.size() : 0; }
+extern "C" const char* wm_tensor_name(wm_handle* h, int i) {
+  if (!h || i < 0 || i >= (int)h->tensors.size()) return nullptr;
+  return h->tensors[i].name.c_str();
+}
+extern "C" int wm_tensor_info(wm_handle* h, const char* name, size_t* offset, size_t* nbytes, int32_t* dtype) {
+  if (!h || !name) return WM_ERR_INVALID;
+  auto it = h->tindex.find(name);
+  if (it == h->tindex.end()) return fail(h, WM_ERR_INVALID, std::string("unknown tensor ") + name);
+  const TensorInfo& t = h->tensors[it->second];
+  if (offset) *offset = t.offset;
+  if (nbytes) *nbytes = t.nbytes;
+  if (dtype) *dtype = t.dtype;
+  return WM_OK;
+}
+extern "C" size_t wm_weights_nbytes(wm_handle* h) { return h ? h->wbytes : 0; }
+
+static int bind_weights(wm_handle* h) {
+  DecModel& m = h->hm;
+  for (int i = 0; i < h->n_dec; ++i) {
+    std::string p = "dec." + std::to_string(i) + ".";
+    DecLayer& L = m.layers[i];
+    L.ln1_g = wptr<float>(h, p + "ln1_g"); L.ln1_b = wptr<float>(h, p + "ln1_b");
+    L.qkv_w = wptr<__half>(h, p + "qkv_w"); L.qkv_b = wptr<float>(h, p + "qkv_b");
+    L.o_w = wptr<__half>(h, p + "o_w"); L.o_b = wptr<float>(h, p + "o_b");
+    L.ln2_g = wptr<float>(h, p + "ln2_g"); L.ln2_b = wptr<float>(h, p + "ln2_b");
+    L.cq_w = wptr<__half>(h, p + "cq_w"); L.cq_b = wptr<float>(h, p + "cq_b");
+    L.co_w = wptr<__half>(h, p + "co_w"); L.co_b = wptr<float>(h, p + "co_b");
+    L.ln3_g = wptr<float>(h, p + "ln3_g"); L.ln3_b = wptr<float>(h, p + "ln3_b");
+    L.fc1_w = wptr<__half>(h, p + "fc1_w"); L.fc1_b = wptr<float>(h, p + "fc1_b");
+    L.fc2_w = wptr<__half>(h, p + "fc2_w"); L.fc2_b = wptr<float>(h, p + "fc2_b");
+    L.self_k = h->self_k[i]; L.self_v = h->self_v[i]; L.cross_kv = h->cross_kv[i];
+  }
+  m.embed = wptr<__half>(h, "dec.embed");
+  m.pos = wptr<float>(h, "dec.pos");
+  m.lnf_g = wptr<float>(h, "dec.lnf_g"); m.lnf_b = wptr<float>(h, "dec.lnf_b");
+  m.heads_w = wptr<__half>(h, "heads_w"); m.heads_b = wptr<float>(h, "heads_b");
+  CK(cudaMemcpy(h->dm, &m, sizeof m, cudaMemcpyHostToDevice));
+  h->wready = true;
+  return WM_OK;
+}
+
+extern "C" int wm_load_weights(wm_handle* h, const void* blob, size_t nbytes) {
+  if (!h || !blob) return WM_ERR_INVALID;
+  if (h->device < 0) return fail(h, WM_ERR_STATE, "layout-only handle");
+  if (nbytes != h->wbytes) return fail(h, WM_ERR_INVALID, "weight blob size mismatch");
+  CK(cudaSetDevice(h->device));
+  if (h->wdev && !h->wowned) h->wdev = nullptr;
+  if (!h->wdev) { CK(cudaMalloc((void**)&h->wdev, h->wbytes)); h->wowned = true; }
+  CK(cudaMemcpy(h->wdev, blob, nbytes, cudaMemcpyHostToDevice));
+  return bind_weights(h);
+}
+extern "C" int wm_adopt_weights(wm_handle* h, void* device_blob, size_t nbytes) {
+  if (!h || !device_blob) return WM_ERR_INVALID;
+  if (h->device < 0) return fail(h, WM_ERR_STATE, "layout-only handle");
+  if (nbytes != h->wbytes) return fail(h, WM_ERR_INVALID, "weight blob size mismatch");
+  CK(cudaSetDevice(h->device));
+  if (h->wdev && h->wowned) cudaFree(h->wdev);
+  h->wdev = reinterpret_cast<unsigned char*>(device_blob);
+  h->wowned = false;
+  return bind_weights(h);
+}
+
+extern "C" int wm_set_suppress(wm_handle* h, const int32_t* sup, int32_t n_sup, const int32_t* beg, int32_t n_beg) {
+  if (!h) return WM_ERR_INVALID;
+  if (h->device < 0) return fail(h, WM_ERR_STATE, "layout-only handle");
+  CK(cudaSetDevice(h->device));
+  std::vector<uint8_t> mask(h->cfg.vocab_size, 0);
+  for (int i = 0; i < n_sup; ++i) {
+    if (sup[i] < 0 || sup[i] >= h->cfg.vocab_size) return fail(h, WM_ERR_INVALID, "suppress id out of range");
+    mask[sup[i]] |= 1;
+  }
+  for (int i = 0; i < n_beg; ++i) {
+    if (beg[i] < 0 || beg[i] >= h->cfg.vocab_size) return fail(h, WM_ERR_INVALID, "begin-suppress id out of range");
+    mask[beg[i]] |= 2;
+  }
+  CK(cudaMemcpy(h->tok_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice));
+  return WM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frontend + encoder
+// ---------------------------------------------------------------------------------------------
+static int run_encoder(wm_handle* h) {
+  const wm_config& c = h->cfg;
+  const int d = c.d_model, f = c.ffn_dim, S = h->S;
+  cudaStream_t s = h->stream;
+  int64_t* nl = &h->launches[1];
+  EncGemmArgs a;
+  memset(&a, 0, sizeof a);
+  // conv1 (k=3, pad 1) as an implicit GEMM over the time-major mel: row t = frames t-1..t+1
+  a.A = h->x_tm; a.lda = 80; a.W = wptr<__half>(h, "enc.conv1_w"); a.bias = wptr<float>(h, "enc.conv1_b");
+  a.M = kFrames; a.N = d; a.K = 256; a.epi = ENC_EPI_BIAS_GELU_F16; a.out16 = h->h1 + d; a.ldo16 = d;
+  CK(enc_gemm(a, s, nl));
+  // conv2 (k=3, stride 2, pad 1): row t = h1 rows 2t..2t+2 ; + GELU + sinusoid positions
+  memset(&a, 0, sizeof a);
+  a.A = h->h1; a.lda = 2 * d; a.W = wptr<__half>(h, "enc.conv2_w"); a.bias = wptr<float>(h, "enc.conv2_b");
+  a.M = S; a.N = d; a.K = 3 * d; a.epi = ENC_EPI_BIAS_GELU_POS_F32; a.out32 = h->x32; a.ldo32 = d;
+  a.pos = wptr<float>(h, "enc.pos");
+  CK(enc_gemm(a, s, nl));
+  for (int i = 0; i < c.enc_layers; ++i) {
+    std::string p = "enc." + std::to_string(i) + ".";
+    CK(enc_layernorm(h->x32, wptr<float>(h, p + "ln1_g"), wptr<float>(h, p + "ln1_b"), h->ln16, nullptr, S, d, s, nl));
+    memset(&a, 0, sizeof a);
+    a.A = h->ln16; a.lda = d; a.W = wptr<__half>(h, p + "qkv_w"); a.bias = wptr<float>(h, p + "qkv_b");
+    a.M = S; a.N = 3 * d; a.K = d; a.epi = ENC_EPI_BIAS_F16; a.out16 = h->qkv16; a.ldo16 = 3 * d;
+    CK(enc_gemm(a, s, nl));
+    CK(enc_attention(h->qkv16, h->att16, S, d, c.n_heads, s, nl));
+    memset(&a, 0, sizeof a);
+    a.A = h->att16; a.lda = d; a.W = wptr<__half>(h, p + "o_w"); a.bias = wptr<float>(h, p + "o_b");
+    a.M = S; a.N = d; a.K = d; a.epi = ENC_EPI_BIAS_RES_F32; a.out32 = h->x32; a.ldo32 = d;
+    CK(enc_gemm(a, s, nl));
+    CK(enc_layernorm(h->x32, wptr<float>(h, p + "ln2_g"), wptr<float>(h, p + "ln2_b"), h->ln16, nullptr, S, d, s, nl));
+    memset(&a, 0, sizeof a);
+    a.A = h->ln16; a.lda = d; a.W = wptr<__half>(h, p + "fc1_w"); a.bias = wptr<float>(h, p + "fc1_b");
+    a.M = S; a.N = f; a.K = d; a.epi = ENC_EPI_BIAS_GELU_F16; a.out16 = h->ffn16; a.ldo16 = f;
+    CK(enc_gemm(a, s, nl));
+    memset(&a, 0, sizeof a);
+    a.A = h->ffn16; a.lda = f; a.W = wptr<__half>(h, p + "fc2_w"); a.bias = wptr<float>(h, p + "fc2_b");
+    a.M = S; a.N = d; a.K = f; a.epi = ENC_EPI_BIAS_RES_F32; a.out32 = h->x32; a.ldo32 = d;
+    CK(enc_gemm(a, s, nl));
+  }
+  CK(enc_layernorm(h->x32, wptr<float>(h, "enc.lnf_g"), wptr<float>(h, "enc.lnf_b"), h->enc16, h->enc32, S, d, s, nl));
+  // cross-attention K/V of every decoder layer, written in the decode layout [pos][k | v]
+  for (int i = 0; i < h->n_dec; ++i) {
+    std::string p = "dec." + std::to_string(i) + ".";
+    memset(&a, 0, sizeof a);
+    a.A = h->enc16; a.lda = d; a.W = wptr<__half>(h, p + "ckv_w"); a.bias = wptr<float>(h, p + "ckv_b");
+    a.M = S; a.N = 2 * d; a.K = d; a.epi = ENC_EPI_BIAS_F16; a.out16 = h->cross_kv[i]; a.ldo16 = 2 * d;
+    CK(enc_gemm(a, s, nl));
+  }
+  return WM_OK;
+}
+
+static int finish_encode(wm_handle* h) {
+  CK(cudaEventRecord(h->ev[2], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float t0 = 0, t1 = 0;
+  CK(cudaEventElapsedTime(&t0, h->ev[0], h->ev[1]));
+  CK(cudaEventElapsedTime(&t1, h->ev[1], h->ev[2]));
+  h->ms[0] = t0; h->ms[1] = t1;
+  h->encoded = true;
+  return WM_OK;
+}
+
+extern "C" int wm_encode_pcm(wm_handle* h, const float* pcm, int32_t n) {
+  if (!h || !pcm || n < 0) return WM_ERR_INVALID;
+  if (!h->wready) return fail(h, WM_ERR_STATE, "weights not loaded");
+  CK(cudaSetDevice(h->device));
+  h->launches[0] = h->launches[1] = 0;
+  const int m = n < kSamples ? n : kSamples;
+  memcpy(h->h_stage, pcm, (size_t)m * sizeof(float));
+  if (m < kSamples) memset(h->h_stage + m, 0, (size_t)(kSamples - m) * sizeof(float));
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  CK(cudaMemcpyAsync(h->pcm, h->h_stage, (size_t)kSamples * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(mel_forward(h->pcm, h->melfb, h->mel32, h->x_tm, h->gmax, h->stream, &h->launches[0]));
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  int r = run_encoder(h);
+  if (r != WM_OK) return r;
+  return finish_encode(h);
+}
+
+extern "C" int wm_encode_mel(wm_handle* h, const float* mel) {
+  if (!h || !mel) return WM_ERR_INVALID;
+  if (!h->wready) return fail(h, WM_ERR_STATE, "weights not loaded");
+  CK(cudaSetDevice(h->device));
+  h->launches[0] = h->launches[1] = 0;
+  memcpy(h->h_stage, mel, (size_t)80 * kFrames * sizeof(float));
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  CK(cudaMemcpyAsync(h->mel32, h->h_stage, (size_t)80 * kFrames * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(mel_to_time_major(h->mel32, h->x_tm, h->stream, &h->launches[0]));
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  int r = run_encoder(h);
+  if (r != WM_OK) return r;
+  return finish_encode(h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode loop
+// ---------------------------------------------------------------------------------------------
+static int get_graph(wm_handle* h, int mode, int T, cudaGraphExec_t* out, int64_t* n_launch) {
+  if (mode == 1 && h->graph_b) { *out = h->graph_b; *n_launch = h->launches_b; return WM_OK; }
+  if (mode == 0) {
+    auto it = h->graph_a.find(T);
+    if (it != h->graph_a.end()) { *out = it->second; *n_launch = h->launches_a[T]; return WM_OK; }
+  }
+  cudaGraph_t g;
+  int64_t nl = 0;
+  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  cudaError_t e = dec_enqueue_pass(h->dm, h->hi, mode, T, h->stream, &nl);
+  cudaError_t e2 = cudaStreamEndCapture(h->stream, &g);
+  CK(e);
+  CK(e2);
+  cudaGraphExec_t ge;
+  CK(cudaGraphInstantiate(&ge, g, 0));
+  CK(cudaGraphDestroy(g));
+  if (mode == 1) { h->graph_b = ge; h->launches_b = nl; }
+  else { h->graph_a[T] = ge; h->launches_a[T] = nl; }
+  *out = ge; *n_launch = nl;
+  return WM_OK;
+}
+
+extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt, const wm_gen_params* gp,
+                           int32_t* out_ids, int32_t* n_out, int32_t* accept_lens, int32_t* n_iter) {
+  if (!h || !prompt || !gp || !out_ids || !n_out) return WM_ERR_INVALID;
+  if (!h->encoded) return fail(h, WM_ERR_STATE, "wm_encode_* must be called before wm_generate");
+  const int K = h->cfg.medusa_num_heads;
+  if (n_prompt < 1 || n_prompt > WM_MAX_T) return fail(h, WM_ERR_INVALID, "prompt length must be in [1, 16]");
+  if (gp->max_length > h->cfg.max_target_positions) return fail(h, WM_ERR_INVALID, "max_length exceeds max_target_positions");
+  if (gp->temperature < 0.f) return fail(h, WM_ERR_INVALID, "temperature must be >= 0");
+  for (int i = 0; i < n_prompt; ++i)
+    if (prompt[i] < 0 || prompt[i] >= h->cfg.vocab_size) return fail(h, WM_ERR_INVALID, "prompt id out of range");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  h->launches[2] = 0;
+
+  // EOS exponential-decay penalty table (HF logits_process.py:1742-1772): indexed by cur_len
+  if (gp->penalty_start != h->last_pen_start || gp->penalty_factor != h->last_pen_factor || n_prompt != h->last_pen_prompt) {
+    std::vector<float> tab(WM_MAX_POS + 32, 0.f);
+    if (gp->penalty_start >= 0) {
+      const int reg = gp->penalty_start + n_prompt;
+      for (int L = 0; L < (int)tab.size(); ++L)
+        if (L > reg) tab[L] = (float)(std::pow((double)gp->penalty_factor, (double)(L - reg)) - 1.0);
+    }
+    CK(cudaMemcpyAsync(h->pen_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    h->last_pen_start = gp->penalty_start; h->last_pen_factor = gp->penalty_factor; h->last_pen_prompt = n_prompt;
+  }
+  // loop state
+  {
+    static thread_local DecState hs;
+    memset(&hs, 0, sizeof hs);
+    hs.L = n_prompt; hs.kv_len = 0; hs.done = 0; hs.n_iter = 0; hs.max_iters = gp->max_iters;
+    hs.max_length = gp->max_length; hs.eos = gp->eos_token_id; hs.pad = gp->pad_token_id;
+    hs.begin_index = gp->begin_index; hs.temperature = gp->temperature; hs.post_thr = gp->posterior_threshold;
+    hs.post_alpha = gp->posterior_alpha;
+    for (int i = 0; i < n_prompt; ++i) hs.ids[i] = prompt[i];
+    // reference stop rule evaluated before the first iteration is never true for sane inputs; the
+    // loop always runs at least once (model.py:635).
+    CK(cudaMemcpyAsync(h->st, &hs, sizeof hs, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->bar, 0, 8 * sizeof(unsigned int), s));
+    CK(cudaStreamSynchronize(s));
+  }
+  cudaGraphExec_t gA1 = nullptr, gAp = nullptr, gB = nullptr;
+  int64_t nA1 = 0, nAp = 0, nB = 0;
+  if (h->decode_mode == 0) {
+    int r;
+    if ((r = get_graph(h, 0, n_prompt, &gAp, &nAp)) != WM_OK) return r;
+    if ((r = get_graph(h, 0, 1, &gA1, &nA1)) != WM_OK) return r;
+    if ((r = get_graph(h, 1, K + 1, &gB, &nB)) != WM_OK) return r;
+  }
+  CK(cudaEventRecord(h->ev[3], s));
+  int L = n_prompt, iters = 0, done = 0;
+  while (!done) {
+    // iterations that are certainly needed unless EOS shows up: each adds at most K+1 tokens and
+    // the loop ends once L + K >= max_length
+    int lb = (gp->max_length - K - L + K) / (K + 1);
+    if (lb < 1) lb = 1;
+    if (lb > 32) lb = 32;
+    if (gp->max_iters > 0 && lb > gp->max_iters - iters) lb = gp->max_iters - iters;
+    if (lb < 1) lb = 1;
+    for (int i = 0; i < lb; ++i) {
+      if (h->decode_mode == 0) {
+        const bool first = (iters + i == 0);
+        CK(cudaGraphLaunch(first ? gAp : gA1, s));
+        CK(cudaGraphLaunch(gB, s));
+        h->launches[2] += (first ? nAp : nA1) + nB;
+      } else {
+        CK(dec_launch_iteration(h->dm, h->hi, s));
+        h->launches[2] += 1;
+      }
+    }
+    CK(cudaMemcpyAsync(h->h_state, h->st, 16 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    L = h->h_state[0];
+    done = h->h_state[2];
+    iters = h->h_state[3];
+  }
+  CK(cudaEventRecord(h->ev[4], s));
+  CK(cudaStreamSynchronize(s));
+  float tms = 0;
+  CK(cudaEventElapsedTime(&tms, h->ev[3], h->ev[4]));
+  h->ms[2] = tms;
+  // read back ids / accept lengths
+  std::vector<int> ids(L);
+  CK(cudaMemcpy(ids.data(), reinterpret_cast<const char*>(h->st) + offsetof(DecState, ids), (size_t)L * sizeof(int),
+                cudaMemcpyDeviceToHost));
+  // post-EOS fill (model.py:798-810)
+  for (int i = 0; i < L; ++i)
+    if (ids[i] == gp->eos_token_id) {
+      for (int j = i + 1; j < L; ++j) ids[j] = gp->eos_token_id;
+      break;
+    }
+  for (int i = 0; i < L; ++i) out_ids[i] = ids[i];
+  *n_out = L;
+  if (n_iter) *n_iter = iters;
+  if (accept_lens && iters > 0)
+    CK(cudaMemcpy(accept_lens, reinterpret_cast<const char*>(h->st) + offsetof(DecState, accept_hist),
+                  (size_t)iters * sizeof(int), cudaMemcpyDeviceToHost));
+  return WM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// taps
+// ---------------------------------------------------------------------------------------------
+extern "C" int wm_get_mel(wm_handle* h, float* out) {
+  if (!h || !out) return WM_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(out, h->mel32, (size_t)80 * kFrames * sizeof(float), cudaMemcpyDeviceToHost));
+  return WM_OK;
+}
+extern "C" int wm_get_encoder_out(wm_handle* h, float* out) {
+  if (!h || !out) return WM_ERR_INVALID;
+  if (!h->encoded) return fail(h, WM_ERR_STATE, "nothing encoded yet");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(out, h->enc32, (size_t)h->S * h->cfg.d_model * sizeof(float), cudaMemcpyDeviceToHost));
+  return WM_OK;
+}
+extern "C" int wm_last_logits(wm_handle* h, int32_t which, float* out) {
+  if (!h || !out || which < 0 || which > 1) return WM_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const size_t n = (size_t)(h->cfg.medusa_num_heads + 1) * h->cfg.vocab_size;
+  CK(cudaMemcpy(out, which == 0 ? h->hm.logits_a : h->hm.logits_b, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return WM_OK;
+}
+extern "C" double wm_last_ms(wm_handle* h, int32_t what) { return (h && what >= 0 && what < 3) ? h->ms[what] : -1.0; }
+extern "C" int64_t wm_last_launches(wm_handle* h, int32_t what) {
+  if (!h) return -1;
+  if (what == 1) return h->launches[0] + h->launches[1];
+  if (what == 2) return h->launches[2];
+  return -1;
+}
+extern "C" int wm_set_decode_mode(wm_handle* h, int32_t mode) {
+  if (!h) return WM_ERR_INVALID;
+  int prev = h->decode_mode;
+  if (mode == 0 || mode == 1) h->decode_mode = mode;
+  return prev;
+}

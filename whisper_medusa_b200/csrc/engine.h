@@ -1,0 +1,53 @@
+// Engine-internal launcher declarations (host side). Not part of the public C ABI.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wm {
+
+struct DecModel;
+
+struct DecHostInfo {
+  int n_sm;
+  int H, K, n_layers, has_block;
+  size_t smem;
+};
+
+// ---- decode.cu ----
+size_t dec_smem_bytes(int d, int ffn);
+cudaError_t dec_configure(size_t smem);
+cudaError_t dec_enqueue_pass(const DecModel* dm, const DecHostInfo& hi, int mode, int T, cudaStream_t s, int64_t* n_launch);
+cudaError_t dec_launch_iteration(const DecModel* dm, const DecHostInfo& hi, cudaStream_t s);
+
+// ---- mel.cu ----
+// pcm: device f32 [480000] (already zero padded). Outputs: mel_f32 [80][3000], xT fp16 [rows>=3000+?][80]
+// time-major with one leading zero row (conv padding); gmax_bits: device scratch (1 int).
+cudaError_t mel_forward(const float* pcm, const float* filters /*[201][80]*/, float* mel_f32, __half* x_tm,
+                        int* gmax_bits, cudaStream_t s, int64_t* n_launch);
+// mel given by the caller: mel_f32 [80][3000] device -> x_tm
+cudaError_t mel_to_time_major(const float* mel_f32, __half* x_tm, cudaStream_t s, int64_t* n_launch);
+
+// ---- enc_gemm.cu ----
+enum EncEpi { ENC_EPI_BIAS_F16 = 0, ENC_EPI_BIAS_GELU_F16 = 1, ENC_EPI_BIAS_RES_F32 = 2, ENC_EPI_BIAS_GELU_POS_F32 = 3 };
+struct EncGemmArgs {
+  const __half* A; int lda;     // [M_pad, K] fp16, row stride lda (elements)
+  const __half* W;              // [N, K] fp16
+  const float* bias;            // [N]
+  int M, N, K;                  // M valid rows; N % 128 == 0; K % 32 == 0
+  int epi;
+  __half* out16; int ldo16;     // fp16 outputs
+  float* out32; int ldo32;      // fp32 residual stream (+=) or plain store
+  const float* pos;             // [M, N] added after GELU (conv2)
+};
+cudaError_t enc_gemm(const EncGemmArgs& a, cudaStream_t s, int64_t* n_launch);
+cudaError_t enc_gemm_configure();
+// LayerNorm rows of fp32 x [M, d] -> fp16 y [M, d] (and optional fp32 copy)
+cudaError_t enc_layernorm(const float* x, const float* g, const float* b, __half* y16, float* y32, int M, int d,
+                          cudaStream_t s, int64_t* n_launch);
+
+// ---- enc_attn.cu ----
+// qkv: fp16 [S_pad, 3d] (q pre-scaled | k | v); out: fp16 [S_pad, d]; full (non-causal) attention over S keys
+cudaError_t enc_attention(const __half* qkv, __half* out, int S, int d, int H, cudaStream_t s, int64_t* n_launch);
+
+}  // namespace wm

@@ -1,0 +1,374 @@
+"""Drop-in host for the reference's decode path: ``WhisperMedusaModel.from_pretrained / .to /
+.generate`` (reference ``whisper_medusa/models/model.py:213``, re-exported at
+``whisper_medusa/__init__.py:1``) over the C ABI in ``include/whisper_medusa_b200.h``.
+
+Same names, argument meaning and error behaviour as the reference for this path:
+
+* ``generate`` asserts batch size 1 (``model.py:1451``);
+* ``return_timestamps`` -> ``NotImplementedError`` (``:1171-1174``); ``no_speech_threshold`` ->
+  ``NotImplementedError`` (``:1201-1204``); more than 3000 feature frames (long-form) ->
+  ``NotImplementedError`` (``:1213-1214``); beam search -> ``Exception`` (``:1153-1156``);
+* the returned ``LongTensor[1, n]`` has the prompt and the trailing EOS stripped (``:1929-1973``).
+
+There is no PyTorch / CPU fallback: every tensor op of the path runs in the CUDA engine, and the
+constructor raises if the engine library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import MedusaConfig, MedusaGenerationConfig
+from .weights import pack_blob
+
+N_FRAMES = 3000
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _check(lib, handle, rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.wm_last_error(handle).decode() if handle else ""
+        raise EngineError(f"{what}: {lib.wm_strerror(rc).decode()} ({rc}) {msg}")
+
+
+class GenerateTrace:
+    """Per-call measurements (the reference collects ``accept_length_list`` but drops it,
+    ``model.py:633,705``)."""
+
+    def __init__(self):
+        self.accept_lengths: List[int] = []
+        self.iterations = 0
+        self.sequences: List[int] = []       # prompt + generated, after the post-EOS fill
+        self.n_new_tokens = 0                 # effective decoded tokens (up to and incl. first EOS)
+        self.ms_mel = self.ms_encoder = self.ms_decode = 0.0
+        self.launches_encode = self.launches_decode = 0
+
+
+class WhisperMedusaModel:
+    """Whisper + Medusa heads, inference only, CUDA engine behind the reference's API."""
+
+    def __init__(self, config: MedusaConfig, state_dict: Optional[Dict[str, torch.Tensor]] = None):
+        _lib.load()  # fail loudly here, not at first generate
+        self.config = config
+        self.generation_config = MedusaGenerationConfig.from_model_config(config)   # model.py:258-263
+        self.generation_config.update(**{k: v for k, v in config.to_dict().items()
+                                         if k in ("posterior_threshold", "posterior_alpha")})
+        self._state_dict = state_dict
+        self._handle = None
+        self._device: Optional[torch.device] = None
+        self._wblob_dev: Optional[torch.Tensor] = None
+        self.last_trace = GenerateTrace()
+        if config.medusa_choices and any(int(c) != 1 for c in config.medusa_choices):
+            raise NotImplementedError(
+                "the CUDA engine implements top-1 chains (medusa_choices all 1), the only configuration "
+                "the reference ships (README.md:181); branching choices are listed under 'next' in DESIGN.md")
+        if len(config.medusa_choices) != config.medusa_num_heads + 1:
+            raise ValueError("len(medusa_choices) must be medusa_num_heads + 1")
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, *args, **kwargs) -> "WhisperMedusaModel":
+        """Reference ``model.py:265-291``: config.json (+ generation_config.json) + model.safetensors."""
+        path = pretrained_model_name_or_path
+        if not os.path.isdir(path):
+            raise OSError(f"{path} is not a local directory (hub access is not available)")
+        config = MedusaConfig.from_pretrained(path)
+        from safetensors.torch import load_file
+
+        st_file = os.path.join(path, "model.safetensors")
+        if not os.path.isfile(st_file):
+            raise OSError(f"{st_file} not found")
+        sd = load_file(st_file)
+        if "whisper_model.proj_out.weight" not in sd:  # tied weight is not serialised by safetensors
+            sd["whisper_model.proj_out.weight"] = sd["whisper_model.model.decoder.embed_tokens.weight"]
+        model = cls(config, sd)
+        try:
+            model.generation_config = MedusaGenerationConfig.from_pretrained(path)
+        except OSError:
+            pass  # reference model.py:286-290
+        return model
+
+    def save_pretrained(self, path: str) -> None:
+        from safetensors.torch import save_file
+
+        if self._state_dict is None:
+            raise RuntimeError("state dict was released")
+        os.makedirs(path, exist_ok=True)
+        self.config.save_pretrained(path)
+        self.generation_config.save_pretrained(path)
+        sd = {k: v.contiguous() for k, v in self._state_dict.items() if k != "whisper_model.proj_out.weight"}
+        save_file(sd, os.path.join(path, "model.safetensors"))
+
+    def get_medusa_choice(self):
+        return self.config.medusa_choices
+
+    @property
+    def device(self) -> torch.device:
+        return self._device if self._device is not None else torch.device("cpu")
+
+    # ------------------------------------------------------------------ engine
+    def _wm_config(self) -> _lib.WmConfig:
+        c = self.config
+        if c.encoder_attention_heads != c.decoder_attention_heads or c.encoder_ffn_dim != c.decoder_ffn_dim:
+            raise NotImplementedError("encoder and decoder must share heads / ffn width (true for every Whisper size)")
+        return _lib.WmConfig(
+            vocab_size=c.vocab_size, d_model=c.d_model, n_heads=c.decoder_attention_heads, ffn_dim=c.decoder_ffn_dim,
+            enc_layers=c.encoder_layers, dec_layers=c.decoder_layers, n_mels=c.num_mel_bins,
+            max_source_positions=c.max_source_positions, max_target_positions=c.max_target_positions,
+            medusa_num_heads=c.medusa_num_heads, medusa_block=1 if c.is_block else 0)
+
+    def to(self, device: Union[str, torch.device], broadcast_src: Optional[int] = None) -> "WhisperMedusaModel":
+        """Create the engine on ``device`` and upload the packed weights.
+
+        With ``broadcast_src`` (inside an initialised ``torch.distributed`` NCCL group) only that rank
+        packs the checkpoint; the blob reaches the other GPUs with one NCCL broadcast over NVLink and
+        the engine adopts the device buffer (``wm_adopt_weights``) -- the only collective of the path.
+        """
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise EngineError("WhisperMedusaModel (B200 engine) runs on CUDA devices only; there is no CPU path")
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        lib = _lib.load()
+        if self._handle is not None:
+            if self._device == torch.device("cuda", index):
+                return self
+            self.close()
+        handle = C.c_void_p()
+        cfg = self._wm_config()
+        rc = lib.wm_create(C.byref(cfg), index, C.byref(handle))
+        if rc != 0:
+            msg = lib.wm_last_error(handle).decode() if handle else ""
+            if handle:
+                lib.wm_destroy(handle)
+            raise EngineError(f"wm_create: {lib.wm_strerror(rc).decode()} {msg}")
+        self._handle = handle
+        self._device = torch.device("cuda", index)
+        nbytes = lib.wm_weights_nbytes(handle)
+        if broadcast_src is None:
+            if self._state_dict is None:
+                raise RuntimeError("no state dict to upload")
+            blob = pack_blob(handle, self.config, self._state_dict)
+            _check(lib, handle, lib.wm_load_weights(handle, C.c_void_p(blob.data_ptr()), nbytes), "wm_load_weights")
+        else:
+            import torch.distributed as dist
+
+            with torch.cuda.device(index):
+                dev_blob = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
+                if dist.get_rank() == broadcast_src:
+                    blob = pack_blob(handle, self.config, self._state_dict)
+                    dev_blob.copy_(blob)
+                dist.broadcast(dev_blob, src=broadcast_src)
+                torch.cuda.synchronize(index)
+            self._wblob_dev = dev_blob  # keep alive: the engine does not own it
+            _check(lib, handle, lib.wm_adopt_weights(handle, C.c_void_p(dev_blob.data_ptr()), nbytes), "wm_adopt_weights")
+        self._push_suppress()
+        return self
+
+    def cuda(self, index: int = 0) -> "WhisperMedusaModel":
+        return self.to(torch.device("cuda", index))
+
+    def eval(self) -> "WhisperMedusaModel":
+        return self
+
+    def release_state_dict(self) -> None:
+        """Drop the host copy of the checkpoint once it is on the device."""
+        self._state_dict = None
+
+    def close(self) -> None:
+        if self._handle is not None:
+            _lib.load().wm_destroy(self._handle)
+            self._handle = None
+            self._wblob_dev = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_decode_mode(self, mode: str) -> None:
+        """``"graph"``: one CUDA graph of stage kernels per pass; ``"persistent"``: one cooperative
+        kernel per speculative iteration."""
+        self._require_engine()
+        _lib.load().wm_set_decode_mode(self._handle, {"graph": 0, "persistent": 1}[mode])
+
+    def _require_engine(self):
+        if self._handle is None:
+            raise EngineError("call .to('cuda') first: the model has no CPU execution path")
+
+    def _push_suppress(self):
+        lib = _lib.load()
+        g = self.generation_config
+        sup = list(g.suppress_tokens or [])
+        beg = list(g.begin_suppress_tokens or [])
+        a = (C.c_int32 * max(1, len(sup)))(*sup)
+        b = (C.c_int32 * max(1, len(beg)))(*beg)
+        _check(lib, self._handle, lib.wm_set_suppress(self._handle, a, len(sup), b, len(beg)), "wm_set_suppress")
+        self._pushed = (tuple(sup), tuple(beg))
+
+    # ------------------------------------------------------------------ generate
+    def _init_tokens(self, language: Optional[str], task: Optional[str]) -> List[int]:
+        """Prompt ids for the supported cases of HF ``generation_whisper.py:1455-1608``."""
+        g = self.generation_config
+        toks = [int(g.decoder_start_token_id)]
+        if g.is_multilingual:
+            if language is None:
+                raise NotImplementedError(
+                    "language detection (an extra encoder+decoder pass, generation_whisper.py:1559-1566) is not "
+                    "implemented; pass language=... as the reference's README/eval script do")
+            key = language if language.startswith("<|") else f"<|{language}|>"
+            if key not in g.lang_to_id:
+                raise ValueError(f"unsupported language {language!r}; known: {sorted(g.lang_to_id)}")
+            toks.append(int(g.lang_to_id[key]))
+            toks.append(int(g.task_to_id[task or "transcribe"]))
+        elif language is not None or task is not None:
+            raise ValueError("Cannot specify `task` or `language` for an English-only model")
+        toks.append(int(g.no_timestamps_token_id))
+        return toks
+
+    def _gen_params(self, prompt_len: int, exponential_decay_length_penalty, max_length, temperature,
+                    max_iters) -> _lib.WmGenParams:
+        g = self.generation_config
+        pen = exponential_decay_length_penalty if exponential_decay_length_penalty is not None \
+            else g.exponential_decay_length_penalty
+        return _lib.WmGenParams(
+            max_length=int(max_length if max_length is not None else g.max_length),
+            eos_token_id=int(g.eos_token_id), pad_token_id=int(g.pad_token_id), begin_index=prompt_len,
+            temperature=float(temperature), posterior_threshold=float(g.posterior_threshold),
+            posterior_alpha=float(g.posterior_alpha),
+            penalty_start=int(pen[0]) if pen is not None else -1,
+            penalty_factor=float(pen[1]) if pen is not None else 1.0,
+            max_iters=int(max_iters or 0))
+
+    def _run_loop(self, prompt: Sequence[int], gp: _lib.WmGenParams) -> GenerateTrace:
+        lib = _lib.load()
+        cap = int(gp.max_length) + self.config.medusa_num_heads + 8
+        out = (C.c_int32 * cap)()
+        acc = (C.c_int32 * cap)()
+        n_out, n_iter = C.c_int32(0), C.c_int32(0)
+        p = (C.c_int32 * len(prompt))(*prompt)
+        _check(lib, self._handle,
+               lib.wm_generate(self._handle, p, len(prompt), C.byref(gp), out, C.byref(n_out), acc, C.byref(n_iter)),
+               "wm_generate")
+        tr = GenerateTrace()
+        tr.sequences = list(out[: n_out.value])
+        tr.accept_lengths = list(acc[: n_iter.value])
+        tr.iterations = n_iter.value
+        gen = tr.sequences[len(prompt):]
+        eos = int(gp.eos_token_id)
+        tr.n_new_tokens = gen.index(eos) + 1 if eos in gen else len(gen)
+        tr.ms_mel, tr.ms_encoder, tr.ms_decode = (lib.wm_last_ms(self._handle, i) for i in range(3))
+        tr.launches_encode = lib.wm_last_launches(self._handle, 1)
+        tr.launches_decode = lib.wm_last_launches(self._handle, 2)
+        return tr
+
+    @staticmethod
+    def _strip(sequences: Sequence[int], prompt_len: int, pad: int, eos: int) -> List[int]:
+        """Reference ``model.py:1929`` (drop prompt) + ``:1950-1973`` (drop trailing pad / EOS)."""
+        seq = list(sequences[prompt_len:])
+        if seq and seq[-1] == pad:
+            n_pad = sum(1 for t in seq if t == pad)
+            if pad == eos:
+                n_pad -= 1
+            if n_pad != 0:
+                seq = seq[:-n_pad]
+        if seq and seq[-1] == eos:
+            seq = seq[:-1]
+        return seq
+
+    def generate(self, input_features: Optional[torch.Tensor] = None, generation_config=None, logits_processor=None,
+                 stopping_criteria=None, prefix_allowed_tokens_fn=None, synced_gpus: bool = False,
+                 return_timestamps: Optional[bool] = None, task: Optional[str] = None, language: Optional[str] = None,
+                 is_multilingual: Optional[bool] = None, prompt_ids=None, prompt_condition_type=None,
+                 condition_on_prev_tokens=None, temperature=None, compression_ratio_threshold=None,
+                 logprob_threshold=None, no_speech_threshold=None, num_segment_frames=None, attention_mask=None,
+                 time_precision: float = 0.02, return_token_timestamps=None, return_segments: bool = False,
+                 return_dict_in_generate=None, **kwargs) -> torch.Tensor:
+        """Transcribe one <= 30 s clip given its log-mel features ``[1, 80, 3000]``
+        (reference ``model.py:1419-1779``); returns ``LongTensor[1, n]``."""
+        self._require_engine()
+        if input_features is None:
+            raise ValueError("input_features is required")
+        assert input_features.shape[0] == 1, "Batch size should be 1 for medusa generation"   # model.py:1451
+        if return_timestamps is True or getattr(self.generation_config, "return_timestamps", False) is True:
+            raise NotImplementedError("return_timestamps is not supported with medusa for now")       # :1171
+        nst = no_speech_threshold if no_speech_threshold is not None else self.generation_config.no_speech_threshold
+        if nst is not None:
+            raise NotImplementedError("no_speech_detection is not supported with medusa for now")     # :1201
+        if input_features.shape[-1] > N_FRAMES:
+            raise NotImplementedError("Longform generation is not supported yet")                     # :1213
+        if kwargs.get("num_beams", 1) not in (None, 1):
+            raise Exception("Only greedy search is supported with medusa (beam modes raise in the reference, model.py:1153-1156)")
+        for unsupported in (logits_processor, stopping_criteria, prefix_allowed_tokens_fn, prompt_ids):
+            if unsupported:
+                raise NotImplementedError("custom logits processors / stopping criteria / prompt_ids are not implemented")
+        if input_features.shape[-1] != N_FRAMES or input_features.shape[-2] != self.config.num_mel_bins:
+            raise ValueError(f"input_features must be [1, {self.config.num_mel_bins}, {N_FRAMES}] (WhisperProcessor output)")
+        mel = input_features.detach().to("cpu", torch.float32).contiguous()
+        lib = _lib.load()
+        _check(lib, self._handle, lib.wm_encode_mel(self._handle, C.cast(mel.data_ptr(), C.POINTER(C.c_float))),
+               "wm_encode_mel")
+        return self._decode(language, task, kwargs, temperature)
+
+    def generate_from_pcm(self, pcm: Union[np.ndarray, torch.Tensor], language: Optional[str] = None,
+                          task: Optional[str] = None, temperature=None, **kwargs) -> torch.Tensor:
+        """Same as ``generate`` but takes 16 kHz mono f32 PCM and runs the log-mel frontend on the GPU
+        (what ``WhisperProcessor`` does on the CPU in the reference's caller, eval_whisper_medusa.py:46-51)."""
+        self._require_engine()
+        x = torch.as_tensor(pcm).detach().to("cpu", torch.float32).contiguous().reshape(-1)
+        if x.numel() > 480000:
+            raise NotImplementedError("Longform generation is not supported yet")
+        lib = _lib.load()
+        _check(lib, self._handle,
+               lib.wm_encode_pcm(self._handle, C.cast(x.data_ptr(), C.POINTER(C.c_float)), int(x.numel())),
+               "wm_encode_pcm")
+        return self._decode(language, task, kwargs, temperature)
+
+    def _decode(self, language, task, kwargs, temperature) -> torch.Tensor:
+        g = self.generation_config
+        cur = (tuple(g.suppress_tokens or []), tuple(g.begin_suppress_tokens or []))
+        if cur != getattr(self, "_pushed", None):
+            self._push_suppress()
+        prompt = self._init_tokens(language, task)
+        # generate() always runs the loop with temperature 1.0 => typical acceptance (model.py:1878-1881);
+        # `medusa_temperature=0` selects the exact-match branch reachable through _medusa_greedy_search.
+        t = kwargs.pop("medusa_temperature", 1.0)
+        gp = self._gen_params(len(prompt), kwargs.pop("exponential_decay_length_penalty", None),
+                              kwargs.pop("max_length", None), t, kwargs.pop("max_iters", 0))
+        tr = self._run_loop(prompt, gp)
+        self.last_trace = tr
+        out = self._strip(tr.sequences, len(prompt), int(gp.pad_token_id), int(gp.eos_token_id))
+        return torch.tensor([out], dtype=torch.long, device=self._device)
+
+    # ------------------------------------------------------------------ parity taps
+    def last_logits(self, which: int) -> torch.Tensor:
+        self._require_engine()
+        n = (self.config.medusa_num_heads + 1, self.config.vocab_size)
+        out = torch.empty(n, dtype=torch.float32)
+        lib = _lib.load()
+        _check(lib, self._handle, lib.wm_last_logits(self._handle, which, C.cast(out.data_ptr(), C.POINTER(C.c_float))),
+               "wm_last_logits")
+        return out
+
+    def encoder_output(self) -> torch.Tensor:
+        self._require_engine()
+        out = torch.empty(self.config.max_source_positions, self.config.d_model, dtype=torch.float32)
+        lib = _lib.load()
+        _check(lib, self._handle, lib.wm_get_encoder_out(self._handle, C.cast(out.data_ptr(), C.POINTER(C.c_float))),
+               "wm_get_encoder_out")
+        return out
+
+    def mel(self) -> torch.Tensor:
+        self._require_engine()
+        out = torch.empty(self.config.num_mel_bins, N_FRAMES, dtype=torch.float32)
+        lib = _lib.load()
+        _check(lib, self._handle, lib.wm_get_mel(self._handle, C.cast(out.data_ptr(), C.POINTER(C.c_float))), "wm_get_mel")
+        return out
