@@ -154,6 +154,29 @@ def _merge_heads(x: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # a2. encoder
 # --------------------------------------------------------------------------------------
+def _flash_attention_engine_rounding(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, block: int = 64) -> torch.Tensor:
+    """softmax(q k^T) v with the engine's rounding points: the same mathematics as the plain
+    softmax, evaluated in 64-key blocks with a running row maximum, the un-normalised
+    probabilities rounded to fp16 before they multiply V (they are the fp16 operand of the P*V
+    tensor-core MMA in ``enc_attn.cu``), the row sum kept in fp32.  ``q`` already carries the
+    head_dim^-0.5 scaling."""
+    H, S, dh = q.shape
+    s = q @ k.transpose(1, 2)
+    m = torch.full((H, S), float("-inf"))
+    l = torch.zeros(H, S)
+    o = torch.zeros(H, S, dh)
+    for b in range(0, S, block):
+        sb = s[:, :, b : b + block]
+        m_new = torch.maximum(m, sb.max(dim=-1).values)
+        alpha = torch.exp(m - m_new)
+        p = torch.exp(sb - m_new[..., None])
+        l = l * alpha + p.sum(dim=-1)
+        o = o * alpha[..., None] + _r16(p) @ v[:, b : b + block]
+        m = m_new
+    return o / l[..., None]
+
+
+
 def encoder_forward(w: RefWeights, cfg, mel: torch.Tensor, regime: str = "fp32") -> torch.Tensor:
     """``[80, 3000]`` log-mel -> ``[1500, d]`` encoder states.
 
@@ -179,8 +202,11 @@ def encoder_forward(w: RefWeights, cfg, mel: torch.Tensor, regime: str = "fp32")
         k = w.lin(h, f"{lp}.self_attn.k_proj")
         v = w.lin(h, f"{lp}.self_attn.v_proj")
         q, k, v = (_split_heads(rq(t), H) for t in (q, k, v))
-        att = torch.softmax(q @ k.transpose(1, 2), dim=-1)
-        o = _merge_heads(rq(att) @ v)
+        if eng:
+            o = _merge_heads(_flash_attention_engine_rounding(q, k, v))
+        else:
+            att = torch.softmax(q @ k.transpose(1, 2), dim=-1)
+            o = _merge_heads(att @ v)
         x = x + w.lin(rq(o), f"{lp}.self_attn.out_proj")
         h = rq(w.ln(x, f"{lp}.final_layer_norm"))
         h = rq(F.gelu(w.lin(h, f"{lp}.fc1")))

@@ -1,0 +1,164 @@
+"""C-ABI surface and host-side logic that need no GPU: the library loads, exports every symbol the
+header declares, defines a consistent weight layout, and the Python host mirrors the reference's
+error behaviour."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from _wm_paths import ROOT
+from whisper_medusa_b200 import MedusaConfig, WhisperMedusaModel, _lib
+from whisper_medusa_b200.model import EngineError
+from whisper_medusa_b200.synthetic import preset_config, synthetic_state_dict
+from whisper_medusa_b200.weights import engine_tensors, pack_blob
+
+
+def test_library_exports_every_declared_symbol(engine_lib):
+    hdr = open(os.path.join(ROOT, "include", "whisper_medusa_b200.h")).read()
+    declared = set(re.findall(r"\b(wm_[a-z_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(engine_lib, name)
+
+
+def test_strerror_and_null_handles(engine_lib):
+    assert engine_lib.wm_strerror(0) == b"ok"
+    assert b"CUDA" in engine_lib.wm_strerror(-2)
+    assert engine_lib.wm_destroy(None) == 0
+    assert engine_lib.wm_tensor_count(None) == 0
+
+
+def _layout_handle(lib, cfg):
+    m = WhisperMedusaModel(cfg, None)
+    h = C.c_void_p()
+    wc = m._wm_config()
+    assert lib.wm_create(C.byref(wc), -1, C.byref(h)) == 0
+    return h
+
+
+@pytest.mark.parametrize("preset,htype", [("micro", "base_head"), ("micro", "medusa_block"), ("tiny.en", "base_head")])
+def test_weight_layout_and_packing(engine_lib, preset, htype):
+    cfg = preset_config(preset, heads=4, heads_type=htype)
+    sd = synthetic_state_dict(cfg, seed=0)
+    h = _layout_handle(engine_lib, cfg)
+    try:
+        blob = pack_blob(h, cfg, sd)
+        assert blob.numel() == engine_lib.wm_weights_nbytes(h)
+        # non-overlapping, 256-byte aligned tensors
+        spans = []
+        off, nb, dt = C.c_size_t(), C.c_size_t(), C.c_int32()
+        for i in range(engine_lib.wm_tensor_count(h)):
+            name = engine_lib.wm_tensor_name(h, i)
+            assert engine_lib.wm_tensor_info(h, name, C.byref(off), C.byref(nb), C.byref(dt)) == 0
+            assert off.value % 256 == 0
+            spans.append((off.value, off.value + nb.value))
+        spans.sort()
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+        # q/k/v fused without touching the values, k bias zero, conv weights re-ordered [out][kw*in]
+        t = dict(engine_tensors(cfg, sd))
+        d = cfg.d_model
+        assert torch.equal(t["dec.0.qkv_w"][:d], sd["whisper_model.model.decoder.layers.0.self_attn.q_proj.weight"])
+        assert torch.equal(t["dec.0.qkv_w"][2 * d:], sd["whisper_model.model.decoder.layers.0.self_attn.v_proj.weight"])
+        assert torch.count_nonzero(t["dec.0.qkv_b"][d:2 * d]) == 0
+        c1 = sd["whisper_model.model.encoder.conv1.weight"]
+        assert torch.equal(t["enc.conv1_w"][:, 80:160], c1[:, :, 1])
+        assert torch.count_nonzero(t["enc.conv1_w"][:, 240:]) == 0
+        nh = cfg.medusa_num_heads + (0 if cfg.is_block else 1)
+        assert t["heads_w"].shape == (nh * d, d)
+        assert engine_lib.wm_tensor_info(h, b"nope", None, None, None) == -1
+    finally:
+        engine_lib.wm_destroy(h)
+
+
+def test_create_rejects_unsupported_shapes(engine_lib):
+    cfg = preset_config("micro", heads=4)
+    m = WhisperMedusaModel(cfg, None)
+    for field, value in (("d_model", 100), ("n_mels", 128), ("medusa_num_heads", 16), ("max_source_positions", 750)):
+        wc = m._wm_config()
+        setattr(wc, field, value)
+        h = C.c_void_p()
+        assert engine_lib.wm_create(C.byref(wc), -1, C.byref(h)) == -1
+        assert engine_lib.wm_last_error(h)
+        engine_lib.wm_destroy(h)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_silent_cpu_fallback(engine_lib):
+    """Without a GPU the engine must fail loudly, not compute on the host."""
+    cfg = preset_config("micro", heads=4)
+    model = WhisperMedusaModel(cfg, synthetic_state_dict(cfg, seed=0))
+    with pytest.raises(EngineError):
+        model.generate(torch.zeros(1, 80, 3000))
+    with pytest.raises(EngineError):
+        model.to("cpu")
+    with pytest.raises(EngineError):
+        model.to("cuda:0")
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "whisper_medusa_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f
+
+
+def test_config_roundtrip_and_reference_errors(tmp_path):
+    cfg = preset_config("micro", heads=4, heads_type="medusa_block")
+    cfg.save_pretrained(str(tmp_path))
+    back = MedusaConfig.from_pretrained(str(tmp_path))
+    assert back.to_dict() == cfg.to_dict()
+    with pytest.raises(ValueError):
+        MedusaConfig(medusa_heads_type="nope", whisper_model_name="synthetic/whisper-micro")   # model.py:224-228
+    with pytest.raises(OSError):
+        WhisperMedusaModel.from_pretrained(str(tmp_path / "missing"))
+    with pytest.raises(NotImplementedError):
+        WhisperMedusaModel(preset_config("micro", heads=2, medusa_choices=[1, 2, 2]) if False else
+                           MedusaConfig(medusa_num_heads=2, medusa_hidden_size=128, medusa_choices=[1, 2, 2],
+                                        whisper_model_name="synthetic/whisper-micro"), None)
+
+
+def test_checkpoint_directory_roundtrip(tmp_path):
+    """from_pretrained reads the reference's checkpoint layout (config.json + model.safetensors with
+    tied proj_out omitted)."""
+    cfg = preset_config("micro", heads=4)
+    sd = synthetic_state_dict(cfg, seed=3)
+    WhisperMedusaModel(cfg, sd).save_pretrained(str(tmp_path))
+    m = WhisperMedusaModel.from_pretrained(str(tmp_path))
+    assert m.config.to_dict() == cfg.to_dict()
+    assert set(m._state_dict) == set(sd)
+    for k in sd:
+        assert torch.equal(m._state_dict[k], sd[k]), k
+    assert m.generation_config.posterior_threshold == 0.09 and m.generation_config.posterior_alpha == 0.3
+    assert m.get_medusa_choice() == [1] * 5
+
+
+def test_generate_argument_errors_match_reference():
+    cfg = preset_config("micro", heads=4)
+    m = WhisperMedusaModel(cfg, None)
+    m._handle = C.c_void_p(1)  # pretend an engine exists: the argument checks come first
+    try:
+        with pytest.raises(AssertionError):
+            m.generate(torch.zeros(2, 80, 3000))                          # model.py:1451
+        with pytest.raises(NotImplementedError):
+            m.generate(torch.zeros(1, 80, 3000), return_timestamps=True)  # model.py:1171
+        with pytest.raises(NotImplementedError):
+            m.generate(torch.zeros(1, 80, 3000), no_speech_threshold=0.6)  # model.py:1201
+        with pytest.raises(NotImplementedError):
+            m.generate(torch.zeros(1, 80, 6000))                          # model.py:1213
+        with pytest.raises(Exception):
+            m.generate(torch.zeros(1, 80, 3000), num_beams=4)             # model.py:1153
+    finally:
+        m._handle = None
+    big = WhisperMedusaModel(preset_config("large-v2", heads=10), None)
+    assert big._init_tokens("en", None) == [50258, 50259, 50359, 50363]
+    with pytest.raises(NotImplementedError):
+        big._init_tokens(None, None)
+    small = WhisperMedusaModel(preset_config("tiny.en", heads=4), None)
+    assert small._init_tokens(None, None) == [50257, 50362]
+    assert WhisperMedusaModel._strip([1, 2, 5, 6, 9, 9], 2, 9, 9) == [5, 6]

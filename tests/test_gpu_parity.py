@@ -1,0 +1,159 @@
+"""GPU parity tests: the CUDA engine, called through the reference-facing Python host and the C
+ABI, against (i) the committed golden fixtures and (ii) the CPU oracle run on the same seeded
+inputs.  Bars: token ids and accept lengths bit-exact; log-mel within 5e-5; encoder states within
+5e-3 of the engine-regime oracle; raw logits within 1e-3 (fp16-weight regime) of the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _wm_paths import GOLDEN
+from oracle import medusa_ref as M
+from oracle import whisper_ref as W
+from whisper_medusa_b200.synthetic import preset_config, synthetic_audio, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["micro_linear_k4", "micro_block_k10", "micro_linear_k4_t0", "tiny_linear_k4", "tiny_block_k4"]
+
+
+def _load(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    seed, stream, max_len, heads, is_block = [int(v) for v in g["meta"]]
+    preset = {"micro": "micro", "tiny": "tiny.en", "large": "large-v2"}[name.split("_")[0]]
+    cfg = preset_config(preset, heads=heads, heads_type="medusa_block" if is_block else "base_head")
+    pen = None if g["penalty"][0] < 0 else (int(g["penalty"][0]), float(g["penalty"][1]))
+    kw = dict(language="en" if cfg.is_multilingual else None, max_length=max_len,
+              exponential_decay_length_penalty=pen, medusa_temperature=float(g["temperature"]))
+    return g, cfg, seed, stream, kw
+
+
+_MODELS = {}
+
+
+def _model(name):
+    from whisper_medusa_b200 import WhisperMedusaModel
+
+    if name not in _MODELS:
+        for m in _MODELS.values():
+            m[0].close()
+        _MODELS.clear()
+        g, cfg, seed, stream, kw = _load(name)
+        sd = synthetic_state_dict(cfg, seed=seed)
+        model = WhisperMedusaModel(cfg, sd).to("cuda:0")
+        _MODELS[name] = (model, sd)
+    return _MODELS[name]
+
+
+@pytest.mark.parametrize("mode", ["graph", "persistent"])
+@pytest.mark.parametrize("name", SMALL)
+def test_tokens_bit_exact_vs_golden_and_oracle(name, mode):
+    g, cfg, seed, stream, kw = _load(name)
+    model, sd = _model(name)
+    model.set_decode_mode(mode)
+    pcm = synthetic_audio(float(g["audio_seconds"]), stream_id=stream)
+    out = model.generate_from_pcm(pcm, **kw)[0].tolist()
+    assert out == g["tokens"].tolist()
+    assert model.last_trace.accept_lengths == g["accept_lengths"].tolist()
+    assert model.last_trace.sequences == g["sequences"].tolist()
+    # the oracle itself, run here on the same inputs (micro only: seconds on the host cores)
+    if name.startswith("micro"):
+        w = W.RefWeights(sd)
+        mel = torch.from_numpy(W.log_mel_spectrogram(pcm))
+        ref, tr = M.generate(w, cfg, mel, language=kw["language"], regime="engine", max_length=kw["max_length"],
+                             exponential_decay_length_penalty=kw["exponential_decay_length_penalty"],
+                             temperature=kw["medusa_temperature"])
+        assert out == ref and model.last_trace.accept_lengths == tr.accept_lengths
+    # same clip through the reference's entry point: generate(input_features) with CPU-made features
+    feats = torch.from_numpy(W.log_mel_spectrogram(pcm))[None]
+    assert model.generate(feats, **kw)[0].tolist() == out
+
+
+@pytest.mark.parametrize("name", ["micro_linear_k4", "tiny_linear_k4", "tiny_block_k4"])
+def test_mel_encoder_logits_close(name):
+    g, cfg, seed, stream, kw = _load(name)
+    model, sd = _model(name)
+    model.set_decode_mode("graph")
+    pcm = synthetic_audio(float(g["audio_seconds"]), stream_id=stream)
+    for it in (1, 2):
+        model.generate_from_pcm(pcm, max_iters=it, **kw)
+        assert model.last_trace.iterations == it
+        for ab, which in (("A", 0), ("B", 1)):
+            lg = model.last_logits(which).numpy()
+            ref = g[f"logits{ab}{it - 1}_strided"]
+            assert np.abs(lg[:, ::97] - ref).max() < 1e-3, (ab, it)
+            assert np.abs(lg[:, ::97] - g[f"logits{ab}{it - 1}_strided_fp32"]).max() < 2e-2, (ab, it)
+            topi = g[f"logits{ab}{it - 1}_topi"]
+            assert lg.argmax(1).tolist() == topi[:, 0].tolist()
+            rows = np.arange(lg.shape[0])[:, None]
+            assert np.abs(lg[rows, topi] - g[f"logits{ab}{it - 1}_topv"]).max() < 1e-3
+    mel = model.mel().numpy()
+    assert np.abs(mel[:, ::8] - g["mel_sample"]).max() < 5e-5
+    enc = model.encoder_output().numpy()
+    assert np.abs(enc[::50] - g["enc_sample"]).max() < 5e-3
+    assert np.abs(enc[::50] - g["enc_sample_fp32"]).max() < 3e-2
+
+
+def test_frontend_edge_cases():
+    """Empty, very short and maximum-length clips (the extractor pads / truncates to 30 s)."""
+    g, cfg, seed, stream, kw = _load("micro_linear_k4")
+    model, sd = _model("micro_linear_k4")
+    for pcm in (np.zeros(0, np.float32), synthetic_audio(0.05), synthetic_audio(30.0, stream_id=5)):
+        model.generate_from_pcm(pcm, max_iters=1, **kw)
+        assert np.abs(model.mel().numpy() - W.log_mel_spectrogram(pcm)).max() < 5e-5
+    with pytest.raises(NotImplementedError):
+        model.generate_from_pcm(np.zeros(480001, np.float32), **kw)      # long-form, model.py:1213
+
+
+def test_reruns_are_deterministic_and_streams_independent():
+    g, cfg, seed, stream, kw = _load("micro_linear_k4")
+    model, sd = _model("micro_linear_k4")
+    a = synthetic_audio(5.0, stream_id=0)
+    b = synthetic_audio(5.0, stream_id=7)
+    model.set_decode_mode("persistent")
+    ra1 = model.generate_from_pcm(a, **kw)[0].tolist()
+    rb = model.generate_from_pcm(b, **kw)[0].tolist()
+    ra2 = model.generate_from_pcm(a, **kw)[0].tolist()
+    assert ra1 == ra2 == g["tokens"].tolist() and rb != ra1
+    # a second engine on the same device gives the same answer (handles are independent)
+    from whisper_medusa_b200 import WhisperMedusaModel
+
+    other = WhisperMedusaModel(cfg, sd).to("cuda:0")
+    assert other.generate_from_pcm(b, **kw)[0].tolist() == rb
+    other.close()
+
+
+def test_length_properties_large_budget():
+    """Size-independent invariants at the full decode budget: tokens per iteration
+    = accept+1 (or 2 when accept = 0); the loop stops once L + K >= max_length; prompt preserved."""
+    g, cfg, seed, stream, kw = _load("tiny_block_k4")
+    model, sd = _model("tiny_block_k4")
+    kw = dict(kw, max_length=448)
+    model.generate_from_pcm(synthetic_audio(5.0, stream_id=2), **kw)
+    tr = model.last_trace
+    n_prompt = 2
+    assert tr.sequences[:n_prompt] == [50257, 50362]
+    assert len(tr.sequences) - n_prompt == sum(a + 1 if a else 2 for a in tr.accept_lengths)
+    assert len(tr.sequences) + cfg.medusa_num_heads >= 448 or cfg.eos_token_id in tr.sequences
+    assert len(tr.sequences) <= 448 + cfg.medusa_num_heads + 1
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(GOLDEN, "large_linear_k10.npz")), reason="fixture missing")
+@pytest.mark.parametrize("mode", ["persistent", "graph"])
+def test_large_v2_tokens_bit_exact_vs_golden(mode):
+    """BASELINE.json configs[1]: whisper-large-v2 + 10 Medusa-Linear heads, 30 s clip."""
+    g, cfg, seed, stream, kw = _load("large_linear_k10")
+    model, sd = _model("large_linear_k10")
+    model.set_decode_mode(mode)
+    pcm = synthetic_audio(float(g["audio_seconds"]), stream_id=stream)
+    out = model.generate_from_pcm(pcm, **kw)[0].tolist()
+    assert out == g["tokens"].tolist()
+    assert model.last_trace.accept_lengths == g["accept_lengths"].tolist()
+    if mode == "graph":
+        model.generate_from_pcm(pcm, max_iters=1, **kw)
+        for ab, which in (("A", 0), ("B", 1)):
+            lg = model.last_logits(which).numpy()
+            assert np.abs(lg[:, ::97] - g[f"logits{ab}0_strided"]).max() < 1e-3
+        enc = model.encoder_output().numpy()
+        assert np.abs(enc[::50] - g["enc_sample"]).max() < 5e-3

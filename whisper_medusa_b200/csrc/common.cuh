@@ -81,12 +81,12 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 // ---------------------------------------------------------------------------------------
 struct DecLayer {
   const float *ln1_g, *ln1_b;
-  const __half* qkv_w;  // [3d, d]   (q rows pre-scaled by head_dim^-0.5)
+  const __half* qkv_w;  // [3d, d]   (q | k | v rows)
   const float* qkv_b;   // [3d]      (k part zero)
   const __half* o_w;    // [d, d]
   const float* o_b;
   const float *ln2_g, *ln2_b;
-  const __half* cq_w;   // [d, d]    (pre-scaled)
+  const __half* cq_w;   // [d, d]
   const float* cq_b;
   const __half* co_w;   // [d, d]
   const float* co_b;

@@ -332,6 +332,7 @@ __device__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta,
           s = fmaf(s_q[c * 8 + 2 * e + 1], f.y, s);
         }
       }
+      s *= 0.125f;  // head_dim^-0.5 (HF scales q; a power of two, so scaling the score is identical)
       s_p[j] = s;
       lmax = fmaxf(lmax, s);
     }
@@ -436,7 +437,7 @@ __device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta
           s = fmaf(q[cc * 8 + 2 * e + 1], f.y, s);
         }
       }
-      sS[t * WM_CH_MAX + j] = s;
+      sS[t * WM_CH_MAX + j] = s * 0.125f;  // head_dim^-0.5
     }
     __syncthreads();
     // per-row max / exp / sum : warp per row

@@ -1,5 +1,5 @@
 // Encoder self-attention: full (non-causal) softmax(Q K^T) V over S = 1500 positions, head_dim 64
-// (HF modeling_whisper.py:284-357; q is pre-scaled by head_dim^-0.5 through the packed weights).
+// (HF modeling_whisper.py:284-357; the head_dim^-0.5 query scaling is applied to the scores here).
 // Flash-style: one CTA = 64 query rows of one head, 4 warps x 16 rows, 64-key blocks streamed through a
 // double-buffered cp.async pipeline, S and P kept in registers, online softmax in fp32, P rounded
 // to fp16 for the P*V MMA (mma.sync m16n8k16).
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(EA_THREADS) enc_attn_kernel(const __half* __re
     for (int e = 0; e < 4; ++e) o_acc[i][e] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY};
   float l_run[2] = {0.f, 0.f};
-  const float L2E = 1.4426950408889634f;
+  const float L2E = 1.4426950408889634f * 0.125f;  // log2(e) * head_dim^-0.5 (q is NOT pre-scaled)
   const int g = lane >> 2, t = lane & 3;
 
   for (int kb = 0; kb < nkb; ++kb) {

@@ -4,8 +4,9 @@ The blob layout is owned by the C library (``wm_tensor_info``); this module only
 engine tensor is derived from the HF/reference parameters:
 
 * q/k/v projections are fused row-wise into one ``[3d, d]`` matrix; the ``head_dim**-0.5`` query
-  scaling (HF ``modeling_whisper.py`` ``WhisperAttention.forward``: ``q_proj(x) * scaling``) is
-  folded into the q rows and bias -- exact, the factor is a power of two;
+  scaling (HF ``modeling_whisper.py`` ``WhisperAttention.forward``: ``q_proj(x) * scaling``) is NOT
+  folded into the weights (that would round fp16-subnormal weights) -- the attention kernels scale
+  the scores instead, which is identical because the factor is a power of two;
 * ``k_proj`` has no bias (zeros in the fused bias);
 * conv weights ``[out, in, kw]`` are re-ordered to ``[out, kw * in]`` for the implicit GEMM over a
   time-major activation (conv1's K = 240 is zero-padded to 256);
@@ -43,9 +44,8 @@ def engine_tensors(config: MedusaConfig, sd: Dict[str, torch.Tensor]):
         return sd[k].to(torch.float16)
 
     def fused_qkv(p):
-        qw = (f32(f"{p}.q_proj.weight") * scale).to(torch.float16)
-        w = torch.cat([qw, f16(f"{p}.k_proj.weight"), f16(f"{p}.v_proj.weight")], dim=0)
-        b = torch.cat([f32(f"{p}.q_proj.bias") * scale, torch.zeros(d), f32(f"{p}.v_proj.bias")])
+        w = torch.cat([f16(f"{p}.q_proj.weight"), f16(f"{p}.k_proj.weight"), f16(f"{p}.v_proj.weight")], dim=0)
+        b = torch.cat([f32(f"{p}.q_proj.bias"), torch.zeros(d), f32(f"{p}.v_proj.bias")])
         return w, b
 
     enc = "whisper_model.model.encoder"
@@ -91,8 +91,8 @@ def engine_tensors(config: MedusaConfig, sd: Dict[str, torch.Tensor]):
         yield e + "o_b", f32(f"{p}.self_attn.out_proj.bias")
         yield e + "ln2_g", f32(f"{p}.encoder_attn_layer_norm.weight")
         yield e + "ln2_b", f32(f"{p}.encoder_attn_layer_norm.bias")
-        yield e + "cq_w", (f32(f"{p}.encoder_attn.q_proj.weight") * scale).to(torch.float16)
-        yield e + "cq_b", f32(f"{p}.encoder_attn.q_proj.bias") * scale
+        yield e + "cq_w", f16(f"{p}.encoder_attn.q_proj.weight")
+        yield e + "cq_b", f32(f"{p}.encoder_attn.q_proj.bias")
         yield e + "ckv_w", torch.cat([f16(f"{p}.encoder_attn.k_proj.weight"), f16(f"{p}.encoder_attn.v_proj.weight")], 0)
         yield e + "ckv_b", torch.cat([torch.zeros(d), f32(f"{p}.encoder_attn.v_proj.bias")])
         yield e + "co_w", f16(f"{p}.encoder_attn.out_proj.weight")
