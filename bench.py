@@ -39,17 +39,27 @@ import torch  # noqa: E402
 METRIC = "effective decoded tokens/sec (post-verify) Whisper-large-v2+Medusa"
 
 
-def algorithmic_bytes_per_iteration(cfg, n_mean: float) -> float:
-    """fp16 bytes one speculative iteration must move (two dependent sweeps)."""
+def algorithmic_bytes(cfg, iterations: int, sweeps_a: int, n_mean: float):
+    """fp16 bytes the decode loop must move, from the unit figures of SURVEY.md 8(d)
+    (DESIGN.md section 4).  Returns (bytes of THIS engine's schedule, bytes of the reference schedule).
+
+    reference schedule: two decoder sweeps per iteration (pass A + pass B), K+1 head matrices + the
+    base head again, two vocabulary projections.  Engine schedule (sweep elision): one sweep per
+    iteration plus one extra sweep per accept-0 iteration and for the prompt (`sweeps_a`)."""
     d, f, V, K, S = cfg.d_model, cfg.decoder_ffn_dim, cfg.vocab_size, cfg.medusa_num_heads, cfg.max_source_positions
-    layer = (6 * d * d + 2 * d * f) * 2 + 2 * S * d * 2          # weights + cross K/V
+    layer = (6 * d * d + 2 * d * f) * 2 + 2 * S * d * 2          # weights + cross K/V of one layer
     proj = V * d * 2
     head = (d * d + d) * 2
-    kv_row = 2 * d * 2 * cfg.decoder_layers
-    if cfg.is_block:
-        n_l = cfg.decoder_layers + 1
-        return 2 * n_l * layer + 2 * proj + K * head + 2 * (n_l / cfg.decoder_layers) * kv_row * n_mean
-    return 2 * cfg.decoder_layers * layer + 2 * proj + (K + 1) * head + head + 2 * kv_row * n_mean
+    n_l = cfg.decoder_layers + (1 if cfg.is_block else 0)
+    kv_sweep = 2 * d * 2 * n_l * n_mean                            # self-K/V rows read by one sweep
+    sweep = n_l * layer + kv_sweep
+    heads_iter = (K * head) if cfg.is_block else ((K + 1) * head + head)
+    fixed = 2 * proj + heads_iter
+    ref = iterations * (2 * sweep + fixed)
+    eng = iterations * (sweep + fixed) + sweeps_a * sweep
+    if cfg.is_block:                                               # tail re-runs the block layer on one row
+        eng += iterations * (layer + kv_sweep / n_l)
+    return float(eng), float(ref)
 
 
 class ClockSampler:
@@ -101,6 +111,28 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def pick_threads(cfg) -> int:
+    """PyTorch eager on every hardware thread of a large host is far slower than on a subset (the
+    batch-1 decode is DRAM-bound and the thread barrier cost grows); time one vocabulary projection
+    for a few thread counts and keep the fastest.  `cores` in the JSON is what was actually used."""
+    n = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, n) if c <= n})
+    w = torch.randn(cfg.vocab_size, cfg.d_model)
+    x = torch.randn(1, cfg.d_model)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        for _ in range(2):
+            torch.nn.functional.linear(x, w)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            torch.nn.functional.linear(x, w)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
 def cpu_reference_sample(cfg, sd, pcm, max_iters: int, threads: int):
     """Time the CPU oracle (PyTorch eager fp32 restatement of the reference loop: one proj_out per
     head, two passes per iteration, KV concatenation) on a bounded sample of the workload."""
@@ -130,7 +162,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("WM_DECODE_MODE", "persistent"), choices=["graph", "persistent"])
+    ap.add_argument("--mode", default=os.environ.get("WM_DECODE_MODE", "persistent"), choices=["graph", "persistent_simple", "persistent"])
     ap.add_argument("--preset", default="large-v2")
     ap.add_argument("--heads", type=int, default=10)
     ap.add_argument("--heads-type", default="base_head", choices=["base_head", "medusa_block"])
@@ -149,7 +181,7 @@ def main():
                 f"{args.seconds:g} s synthetic 16 kHz audio per stream, greedy/typical acceptance, max_length 448")
     config = {"workload": workload, "streams_per_step": world, "parallelism": f"replicas x{world} (independent streams)",
               "weights": "seeded synthetic fp16 (seed 0)", "l2": "weights (3.1 GB) >> L2: every iteration re-streams them from HBM"}
-    threads = os.cpu_count() or 1
+    threads = pick_threads(cfg) if (args.impl == "reference" or not args.no_cpu_baseline) else (os.cpu_count() or 1)
 
     # ------------------------------------------------------------------ reference arm (CPU oracle)
     if args.impl == "reference":
@@ -212,6 +244,7 @@ def main():
     toks = iters = launches = 0
     dec_ms = enc_ms = mel_ms = 0.0
     n_sum = 0.0
+    sweeps_a = 0
     with ClockSampler(local_rank) as cs:
         t0 = time.perf_counter()
         for i in range(args.warmup, args.warmup + args.steps):
@@ -225,11 +258,12 @@ def main():
             mel_ms += tr.ms_mel
             launches += tr.launches_encode + tr.launches_decode
             n_sum += 0.5 * len(tr.sequences) * tr.iterations   # mean self-KV length over the run ~ L_final / 2
+            sweeps_a += 1 + sum(1 for a in tr.accept_lengths[:-1] if a == 0)   # prompt + one per accept-0 iteration
         barrier()
         wall = time.perf_counter() - t0
     clocks = cs.summary()
 
-    stats = torch.tensor([toks, iters, dec_ms, wall, enc_ms, mel_ms, launches, n_sum], dtype=torch.float64, device=device)
+    stats = torch.tensor([toks, iters, dec_ms, wall, enc_ms, mel_ms, launches, n_sum, sweeps_a], dtype=torch.float64, device=device)
     if dist is not None:
         allv = [torch.zeros_like(stats) for _ in range(world)]
         dist.all_gather(allv, stats)
@@ -248,10 +282,14 @@ def main():
     e2e_value = tot_tok / max_wall
     # roofline of the decode iteration (the dominant kernel: one launch per iteration in persistent mode)
     it0, n_mean = float(allv[0, 1]), float(allv[0, 7]) / max(1.0, float(allv[0, 1]))
-    bytes_iter = algorithmic_bytes_per_iteration(cfg, n_mean)
+    bytes_eng, bytes_ref = algorithmic_bytes(cfg, int(it0), int(allv[0, 8]), n_mean)
+    if args.mode == "graph":
+        pass  # same schedule; the graph mode only differs in how stages are launched
     ms_iter = float(allv[0, 2]) / max(1.0, it0)
-    achieved = bytes_iter / (ms_iter / 1e3) / 1e9
+    achieved = bytes_eng / (float(allv[0, 2]) / 1e3) / 1e9
     peak, peak_src = measured_peak_gbs()
+    tok_iter = tot_tok / max(1.0, tot_iter)
+    ref_roofline_tok_s = peak * 1e9 / (bytes_ref / max(1.0, it0)) * tok_iter   # per GPU
     result = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * max_wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -261,8 +299,12 @@ def main():
         "gpu_launches": int(allv[:, 6].sum()),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "decode iteration (pass A + pass B)",
-                     "algorithmic_bytes_per_iteration": bytes_iter, "ms_per_iteration": ms_iter},
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "dec_iteration_ring_kernel (one launch = one speculative iteration)"
+                     if args.mode == "persistent" else f"decode iteration ({args.mode})",
+                     "algorithmic_bytes_per_iteration": bytes_eng / max(1.0, it0), "ms_per_iteration": ms_iter,
+                     "reference_schedule_bytes_per_iteration": bytes_ref / max(1.0, it0),
+                     "frac_of_reference_schedule_roofline": (value / world) / ref_roofline_tok_s},
         "detail": {"tokens_per_step": tot_tok / (world * args.steps), "iterations_per_step": tot_iter / (world * args.steps),
                    "tokens_per_iteration": tot_tok / max(1.0, tot_iter), "ms_mel": float(allv[0, 5]) / args.steps,
                    "ms_encoder": float(allv[0, 4]) / args.steps, "ms_decode": float(allv[0, 2]) / args.steps},

@@ -115,8 +115,10 @@ int wm_last_logits(wm_handle* h, int32_t which, float* out);
 double wm_last_ms(wm_handle* h, int32_t what);
 /* Number of kernel launches issued by the last wm_encode_* (what=1) / wm_generate (what=2). */
 int64_t wm_last_launches(wm_handle* h, int32_t what);
-/* Decode execution mode: 0 = one graph launch per pass (stage kernels), 1 = persistent
- * cooperative kernel per speculative iteration.  Returns the previous mode. */
+/* Decode execution mode: 0 = CUDA graphs of stage kernels (debug / per-stage profiling), 1 =
+ * persistent cooperative kernel per speculative iteration (grid barriers only), 2 = the same with
+ * the shared-memory weight ring (bulk-async prefetch across barriers; the product path).
+ * Returns the previous mode. */
 int wm_set_decode_mode(wm_handle* h, int32_t mode);
 
 #ifdef __cplusplus

@@ -13,6 +13,8 @@
 
 namespace wm {
 
+struct StageInstr;
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -111,6 +113,7 @@ struct DecState {
   int eos, pad;
   int begin_index;
   int accept_last;
+  int need_a;       // 1 => the newest token is not cached yet: run sweep A before the tail
   float temperature, post_thr, post_alpha;
   int ids[WM_MAX_POS + 32];
   int cand[WM_MAX_T];            // candidate chain of the current iteration (c0, head 1..K)
@@ -141,9 +144,14 @@ struct DecModel {
   float* ffn_h;    // [WM_MAX_T, ffn]
   float* hidden;   // [WM_MAX_T, d]  final-LN output (block type: input of the block)
   float* head_h;   // [WM_MAX_T, d]
+  float* carry;    // [d] final-LN hidden state of the newest cached token (input of the heads)
   float* cross_part;  // [H][WM_CROSS_CHUNKS][WM_MAX_T][WM_HEAD_DIM + 2]
+  unsigned int* cross_cnt;  // [H] arrival counters of the cross-attention chunks (last arriver combines)
   float* logits_a;    // [WM_MAX_T, V]
   float* logits_b;    // [WM_MAX_T, V]
+  // stage program of the persistent ring kernel: {stage, mode, layer} triples; lists [off[i], off[i+1])
+  const struct StageInstr* prog;
+  int prog_off[4];
   DecState* st;
   unsigned int* bar;  // grid-barrier words for the persistent kernel
 };

@@ -11,6 +11,8 @@
 // skinny GEMMs (T <= 16 rows) run on mma.sync m16n8k16 with the fp32 activation split into
 // fp16 hi + lo parts (two MMAs), which keeps ~22 mantissa bits of the activation; the path is
 // HBM-bound (weights are streamed exactly once per pass), not tensor-bound.
+#include <vector>
+
 #include "common.cuh"
 #include "engine.h"
 
@@ -19,6 +21,12 @@ namespace wm {
 // -----------------------------------------------------------------------------------------
 // pass geometry (uniform across the grid; read from the loop state)
 // -----------------------------------------------------------------------------------------
+// MODE_A   : sweep over the tokens that are not cached yet (prompt, or the extra token after an
+//            accept-0 iteration): rows ids[kv_len .. L)
+// MODE_B   : verify sweep over the K+1 candidate tokens at positions L .. L+K
+// MODE_TAIL: block type only -- the medusa block re-run on the carried hidden state of the newest
+//            cached token (position L-1) to feed the heads
+enum { MODE_A = 0, MODE_B = 1, MODE_TAIL = 2 };
 struct PassGeom {
   int T;     // query rows of this pass
   int base;  // position of row 0 (also the self-KV row it writes)
@@ -26,12 +34,15 @@ struct PassGeom {
 __device__ __forceinline__ PassGeom pass_geom(const DecModel* m, int mode) {
   const DecState* st = m->st;
   PassGeom g;
-  if (mode == 0) {
+  if (mode == MODE_A) {
     g.T = st->L - st->kv_len;
     g.base = st->kv_len;
-  } else {
+  } else if (mode == MODE_B) {
     g.T = m->K + 1;
     g.base = st->L;
+  } else {
+    g.T = 1;
+    g.base = st->L - 1;
   }
   return g;
 }
@@ -44,7 +55,7 @@ __device__ void stage_embed(const DecModel* m, int mode, int cta, int ncta) {
   const DecState* st = m->st;
   const int d = m->d;
   for (int t = cta; t < g.T; t += ncta) {
-    int tok = (mode == 0) ? st->ids[g.base + t] : st->cand[t];
+    int tok = (mode == MODE_A) ? st->ids[g.base + t] : st->cand[t];
     const __half* e = m->embed + (size_t)tok * d;
     const float* p = m->pos + (size_t)(g.base + t) * d;
     float* x = m->x + (size_t)t * d;
@@ -405,6 +416,7 @@ __device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta
   float* sM = sQ + WM_MAX_T * 64;                                   // [16] max, [16] sum
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int T = g.T;
+  __shared__ int s_last;
   for (int item = cta; item < H * WM_CROSS_CHUNKS; item += ncta) {
     const int h = item / WM_CROSS_CHUNKS, c = item - h * WM_CROSS_CHUNKS;
     const int j0 = c * CH, nk = max(0, min(S, j0 + CH) - j0);
@@ -484,35 +496,43 @@ __device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta
       }
       if (lane == 0) { out[64] = sM[t]; out[65] = sM[WM_MAX_T + t]; }
     }
-  }
-}
-
-// stage: combine the chunk partials (fixed order => deterministic)
-__device__ void stage_cross_combine(const DecModel* m, int mode, int cta, int ncta) {
-  PassGeom g = pass_geom(m, mode);
-  const int d = m->d;
-  const int total = g.T * d;
-  for (int idx = cta * blockDim.x + threadIdx.x; idx < total; idx += ncta * blockDim.x) {
-    const int t = idx / d, n = idx - t * d;
-    const int h = n >> 6, e = n & 63;
-    const float* base = m->cross_part + ((size_t)h * WM_CROSS_CHUNKS * WM_MAX_T + t) * (WM_HEAD_DIM + 2);
-    const size_t cstride = (size_t)WM_MAX_T * (WM_HEAD_DIM + 2);
-    float M = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < WM_CROSS_CHUNKS; ++c) M = fmaxf(M, base[c * cstride + 64]);
-    float num = 0.f, den = 0.f;
-#pragma unroll
-    for (int c = 0; c < WM_CROSS_CHUNKS; ++c) {
-      const float w = expf(base[c * cstride + 64] - M);
-      num = fmaf(w, base[c * cstride + e], num);
-      den = fmaf(w, base[c * cstride + 65], den);
+    // The chunk that arrives last for this head folds the WM_CROSS_CHUNKS partials (always in chunk
+    // order => deterministic) -- no separate combine stage / grid barrier.
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int prev = atomicAdd(&m->cross_cnt[h], 1u);
+      s_last = (prev == WM_CROSS_CHUNKS - 1) ? 1 : 0;
+      if (s_last) m->cross_cnt[h] = 0u;   // everybody has arrived: re-arm for the next layer
     }
-    m->attn[(size_t)t * d + n] = num / den;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const size_t cstride = (size_t)WM_MAX_T * (WM_HEAD_DIM + 2);
+      for (int idx = tid; idx < T * 64; idx += blockDim.x) {
+        const int t = idx >> 6, e = idx & 63;
+        const float* base = m->cross_part + ((size_t)h * WM_CROSS_CHUNKS * WM_MAX_T + t) * (WM_HEAD_DIM + 2);
+        float M = -INFINITY;
+#pragma unroll
+        for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc) M = fmaxf(M, __ldcg(base + cc * cstride + 64));
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc) {
+          const float w = expf(__ldcg(base + cc * cstride + 64) - M);
+          num = fmaf(w, __ldcg(base + cc * cstride + e), num);
+          den = fmaf(w, __ldcg(base + cc * cstride + 65), den);
+        }
+        m->attn[(size_t)t * d + h * 64 + e] = num / den;
+      }
+    }
   }
 }
 
 // -----------------------------------------------------------------------------------------
-// stage: final LayerNorm -> hidden  (HF modeling_whisper.py:791); block type also seeds the block
+// stage: final LayerNorm -> hidden  (HF modeling_whisper.py:791)
+//   sweep A: the last row is also the "carry" (hidden state of the newest cached token, the
+//            input of the Medusa heads).  sweep B + block type: base logits read the hidden
+//            states directly (reference model.py:1287).
 // -----------------------------------------------------------------------------------------
 __device__ void stage_final_ln(const DecModel* m, int mode, int cta, int ncta) {
   PassGeom g = pass_geom(m, mode);
@@ -530,20 +550,24 @@ __device__ void stage_final_ln(const DecModel* m, int mode, int cta, int ncta) {
     for (int j = lane; j < d; j += 32) {
       const float y = (x[j] - mean) * rstd * m->lnf_g[j] + m->lnf_b[j];
       hid[j] = y;
-      if (m->has_block) {
-        // medusa_block consumes last_hidden_state (reference model.py:1374-1376); base logits use it
-        // directly (model.py:1287).  Pass A: only the last row feeds vocab row 0; pass B: every row.
-        if (mode == 1) m->head_h[(size_t)t * d + j] = y;
-        else if (t == g.T - 1) m->head_h[j] = y;
-      }
+      if (mode == MODE_A && t == g.T - 1) m->carry[j] = y;
+      if (mode == MODE_B && m->has_block) m->head_h[(size_t)t * d + j] = y;
     }
   }
 }
-// block type: residual stream of the extra layer starts from the LayerNorm'ed hidden states
+// block type: the extra layer consumes the LayerNorm'ed hidden states (reference model.py:1374-1376)
 __device__ void stage_copy_hidden_to_x(const DecModel* m, int mode, int cta, int ncta) {
   PassGeom g = pass_geom(m, mode);
   const int total = g.T * m->d;
   for (int idx = cta * blockDim.x + threadIdx.x; idx < total; idx += ncta * blockDim.x) m->x[idx] = m->hidden[idx];
+}
+// block type, tail: the block runs on the carried hidden state (one row); vocab row 0 = base logits
+__device__ void stage_tail_seed(const DecModel* m, int cta, int ncta) {
+  for (int idx = cta * blockDim.x + threadIdx.x; idx < m->d; idx += ncta * blockDim.x) {
+    const float y = m->carry[idx];
+    m->x[idx] = y;
+    m->head_h[idx] = y;
+  }
 }
 
 // -----------------------------------------------------------------------------------------
@@ -639,44 +663,64 @@ __device__ void stage_select(const DecModel* m, int mode, int cta, int ncta, uns
 }
 
 // -----------------------------------------------------------------------------------------
-// stage: accept + bookkeeping (single thread)
+// stage: accept + bookkeeping (CTA 0)
 //   evaluate_posterior (chain => one candidate), update_inference_inputs (medusa_utils.py:630-652),
 //   KV trim (model.py:383-401: chain rows are contiguous => kv_len is just advanced), stop rules
 //   (model.py:774-793).
+//
+//   Sweep elision: the reference re-runs the decoder on the last emitted token (its "pass A") to
+//   get the hidden state the heads read.  When accept >= 1 that token is candidate[accept], which
+//   the verify sweep just processed at the same position behind the same accepted prefix, so its
+//   hidden state and K/V row already exist: we keep accept+1 K/V rows and carry hidden[accept]
+//   instead of recomputing them (identical values, half the weight traffic).  Only after an
+//   accept-0 iteration (second emitted token = argmax of the verify row, never seen by the
+//   decoder) a one-token sweep A is needed (`need_a`).
 // -----------------------------------------------------------------------------------------
 __device__ void stage_accept(const DecModel* m) {
+  __shared__ int s_a;
   DecState* st = m->st;
   const int K = m->K;
-  const int L = st->L;
-  int a = 0;
-  if (st->temperature == 0.f) {
-    while (a < K && st->cand[a + 1] == st->row_argmax[a]) ++a;
-  } else {
-    while (a < K && st->row_pc[a] > st->row_thr[a]) ++a;
+  if (threadIdx.x == 0) {
+    const int L = st->L;
+    int a = 0;
+    if (st->temperature == 0.f) {
+      while (a < K && st->cand[a + 1] == st->row_argmax[a]) ++a;
+    } else {
+      while (a < K && st->row_pc[a] > st->row_thr[a]) ++a;
+    }
+    int n_new = a + 1;
+    for (int i = 0; i <= a; ++i) st->ids[L + i] = st->cand[i];
+    if (a == 0) { st->ids[L + 1] = st->row_argmax[0]; n_new = 2; }
+    bool eos = false;
+    for (int i = 0; i < n_new; ++i) eos |= (st->ids[L + i] == st->eos);
+    const int newL = L + n_new;
+    st->L = newL;
+    st->kv_len = (a == 0) ? newL - 1 : newL;
+    st->need_a = (a == 0) ? 1 : 0;
+    st->accept_last = a;
+    st->accept_hist[st->n_iter] = a;
+    st->n_iter += 1;
+    bool done = eos || newL >= st->max_length || newL + K >= st->max_length;
+    if (st->max_iters > 0 && st->n_iter >= st->max_iters) done = true;
+    if (done) st->done = 1;
+    s_a = a;
   }
-  int n_new = a + 1;
-  for (int i = 0; i <= a; ++i) st->ids[L + i] = st->cand[i];
-  if (a == 0) { st->ids[L + 1] = st->row_argmax[0]; n_new = 2; }
-  bool eos = false;
-  for (int i = 0; i < n_new; ++i) eos |= (st->ids[L + i] == st->eos);
-  const int newL = L + n_new;
-  st->L = newL;
-  st->kv_len = newL - 1;
-  st->accept_last = a;
-  st->accept_hist[st->n_iter] = a;
-  st->n_iter += 1;
-  bool done = eos || newL >= st->max_length || newL + K >= st->max_length;
-  if (st->max_iters > 0 && st->n_iter >= st->max_iters) done = true;
-  if (done) st->done = 1;
+  __syncthreads();
+  const int a = s_a;
+  if (a >= 1) {
+    const float* src = m->hidden + (size_t)a * m->d;
+    for (int j = threadIdx.x; j < m->d; j += blockDim.x) m->carry[j] = src[j];
+  }
 }
 
 // -----------------------------------------------------------------------------------------
 // GEMM descriptors of the stages
 // -----------------------------------------------------------------------------------------
 enum StageId {
-  ST_EMBED = 0, ST_QKV, ST_SELF_ATTN, ST_OPROJ, ST_CROSS_Q, ST_CROSS_ATTN, ST_CROSS_COMBINE, ST_CROSS_O,
-  ST_FC1, ST_FC2, ST_FINAL_LN, ST_COPY_HIDDEN, ST_HEADS, ST_VOCAB, ST_SELECT, ST_ACCEPT
+  ST_EMBED = 0, ST_QKV, ST_SELF_ATTN, ST_OPROJ, ST_CROSS_Q, ST_CROSS_ATTN, ST_CROSS_O,
+  ST_FC1, ST_FC2, ST_FINAL_LN, ST_COPY_HIDDEN, ST_TAIL_SEED, ST_HEADS, ST_VOCAB, ST_SELECT, ST_ACCEPT
 };
+enum PhaseId { PH_SWEEP_A = 0, PH_TAIL = 1, PH_VERIFY = 2 };
 
 __device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mode, int layer) {
   PassGeom pg = pass_geom(m, mode);
@@ -724,14 +768,15 @@ __device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mode, int l
       break;
     case ST_HEADS:
       g.bias = m->heads_b; g.W = m->heads_w; g.K = d; g.xsrc = XS_PLAIN; g.out = m->head_h; g.ldo = d;
-      if (mode == 0) {
-        // pass A: every head on the last position (generate_candidates reads logits[:, -1])
-        g.X = m->has_block ? m->x : m->hidden;
-        g.x_row0 = pg.T - 1; g.x_rows = 1;
+      if (mode == MODE_A) {
+        // tail: every head on the hidden state of the newest token (generate_candidates reads
+        // logits[:, -1]); block type: on the medusa block's output for that token
+        g.X = m->has_block ? m->x : m->carry;
+        g.x_row0 = 0; g.x_rows = 1;
         g.N = (m->has_block ? m->K : m->K + 1) * d;
         g.epi = EPI_HEADS_A; g.out_row0 = m->has_block ? 1 : 0;
       } else {
-        // pass B (base_head type only): head 0 on every tree position (disable_medusa, model.py:1281-1284)
+        // verify (base_head type only): head 0 on every tree position (disable_medusa, model.py:1281-1284)
         g.X = m->hidden; g.N = d; g.epi = EPI_HEAD_B;
       }
       break;
@@ -739,7 +784,7 @@ __device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mode, int l
     default:
       g.W = m->embed; g.N = m->V; g.K = d;
       g.xsrc = XS_PLAIN; g.X = m->head_h; g.x_rows = m->K + 1;
-      g.epi = EPI_LOGITS; g.out = (mode == 0) ? m->logits_a : m->logits_b; g.ldo = m->V;
+      g.epi = EPI_LOGITS; g.out = (mode == MODE_A) ? m->logits_a : m->logits_b; g.ldo = m->V;
       break;
   }
   return g;
@@ -750,11 +795,11 @@ __device__ void run_stage(const DecModel* m, int stage, int mode, int layer, int
     case ST_EMBED: stage_embed(m, mode, cta, ncta); break;
     case ST_SELF_ATTN: stage_self_attn(m, mode, layer, cta, ncta, smem); break;
     case ST_CROSS_ATTN: stage_cross_attn(m, mode, layer, cta, ncta, smem); break;
-    case ST_CROSS_COMBINE: stage_cross_combine(m, mode, cta, ncta); break;
     case ST_FINAL_LN: stage_final_ln(m, mode, cta, ncta); break;
     case ST_COPY_HIDDEN: stage_copy_hidden_to_x(m, mode, cta, ncta); break;
+    case ST_TAIL_SEED: stage_tail_seed(m, cta, ncta); break;
     case ST_SELECT: stage_select(m, mode, cta, ncta, smem); break;
-    case ST_ACCEPT: if (cta == 0 && threadIdx.x == 0) stage_accept(m); break;
+    case ST_ACCEPT: if (cta == 0) stage_accept(m); break;
     default: {
       GemmDesc g = make_gemm_desc(m, stage, mode, layer);
       stage_gemm(g, cta, ncta, smem);
@@ -763,100 +808,120 @@ __device__ void run_stage(const DecModel* m, int stage, int mode, int layer, int
 }
 
 // -----------------------------------------------------------------------------------------
-// mode 0: one kernel per stage (captured into a CUDA graph per pass by the host)
+// stage sequences (one definition shared by the graph builder on the host and the persistent
+// kernel on the device)
+// -----------------------------------------------------------------------------------------
+template <class F>
+__host__ __device__ void seq_layer(int l, int mode, F&& f) {
+  f(ST_QKV, mode, l); f(ST_SELF_ATTN, mode, l); f(ST_OPROJ, mode, l); f(ST_CROSS_Q, mode, l);
+  f(ST_CROSS_ATTN, mode, l); f(ST_CROSS_O, mode, l); f(ST_FC1, mode, l); f(ST_FC2, mode, l);
+}
+// decoder sweep over the rows of `mode` (+ the medusa block's K/V rows for them)
+template <class F>
+__host__ __device__ void seq_sweep(int n_layers, int has_block, int mode, F&& f) {
+  f(ST_EMBED, mode, 0);
+  for (int l = 0; l < n_layers; ++l) seq_layer(l, mode, f);
+  f(ST_FINAL_LN, mode, 0);
+  if (has_block) { f(ST_COPY_HIDDEN, mode, 0); f(ST_QKV, mode, n_layers); }
+}
+// candidates from the carried hidden state: (block on it,) K+1 heads, vocab projection, top-1
+template <class F>
+__host__ __device__ void seq_tail(int n_layers, int has_block, F&& f) {
+  if (has_block) { f(ST_TAIL_SEED, MODE_TAIL, 0); seq_layer(n_layers, MODE_TAIL, f); }
+  f(ST_HEADS, MODE_A, 0); f(ST_VOCAB, MODE_A, 0); f(ST_SELECT, MODE_A, 0);
+}
+// verify: sweep B, base logits of the K+1 positions, acceptance statistics, accept
+template <class F>
+__host__ __device__ void seq_verify(int n_layers, int has_block, F&& f) {
+  seq_sweep(n_layers, has_block, MODE_B, f);
+  if (!has_block) f(ST_HEADS, MODE_B, 0);
+  f(ST_VOCAB, MODE_B, 0); f(ST_SELECT, MODE_B, 0); f(ST_ACCEPT, MODE_B, 0);
+}
+
+// -----------------------------------------------------------------------------------------
+// mode 0: one kernel per stage (captured into CUDA graphs by the host)
 // -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WM_DEC_THREADS, 1)
-dec_stage_kernel(const DecModel* __restrict__ m, int stage, int mode, int layer) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  if (m->st->done) return;
+dec_stage_kernel(const DecModel* __restrict__ m, int stage, int mode, int layer, int phase) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const DecState* st = m->st;
+  if (st->done) return;
+  if (phase == PH_SWEEP_A && !st->need_a) return;
   run_stage(m, stage, mode, layer, blockIdx.x, gridDim.x, smem);
 }
 
 // -----------------------------------------------------------------------------------------
 // mode 1: persistent cooperative kernel -- one launch per speculative iteration
 // -----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// All CTAs are co-resident (cooperative launch).  bar[0] is a monotonically increasing arrival
+// counter (reset by the host before every wm_generate): barrier number e completes when it
+// reaches ncta * e.
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch, int ncta) {
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += 1;
+    const unsigned int target = (unsigned int)ncta * epoch;
     __threadfence();
-    unsigned int prev = atomicAdd(&bar[0], 1u);
-    if (prev == (unsigned int)ncta * epoch - 1u) {
-      // last arriver releases everybody
-      atomicExch(&bar[1], epoch);
-    } else {
-      volatile unsigned int* flag = &bar[1];
-      while (*flag < epoch) { __nanosleep(20); }
-    }
+    atomicAdd(&bar[0], 1u);
+    while (ld_acquire_u32(&bar[0]) < target) { }
     __threadfence();
   }
   __syncthreads();
 }
 
-struct PassPlan {
-  int n_layers_full;  // layers that run completely
-  int has_block;
-};
-
-__device__ void run_pass(const DecModel* m, int mode, int cta, int ncta, unsigned char* smem, unsigned int& epoch) {
-  unsigned int* bar = m->bar;
-#define WM_STAGE(st, layer)                       \
-  run_stage(m, st, mode, layer, cta, ncta, smem); \
-  grid_barrier(bar, epoch, ncta);
-  WM_STAGE(ST_EMBED, 0)
-  for (int l = 0; l < m->n_layers; ++l) {
-    WM_STAGE(ST_QKV, l)
-    WM_STAGE(ST_SELF_ATTN, l)
-    WM_STAGE(ST_OPROJ, l)
-    WM_STAGE(ST_CROSS_Q, l)
-    WM_STAGE(ST_CROSS_ATTN, l)
-    WM_STAGE(ST_CROSS_COMBINE, l)
-    WM_STAGE(ST_CROSS_O, l)
-    WM_STAGE(ST_FC1, l)
-    WM_STAGE(ST_FC2, l)
-  }
-  WM_STAGE(ST_FINAL_LN, 0)
-  if (m->has_block) {
-    const int l = m->n_layers;
-    WM_STAGE(ST_COPY_HIDDEN, 0)
-    WM_STAGE(ST_QKV, l)
-    if (mode == 0) {
-      WM_STAGE(ST_SELF_ATTN, l)
-      WM_STAGE(ST_OPROJ, l)
-      WM_STAGE(ST_CROSS_Q, l)
-      WM_STAGE(ST_CROSS_ATTN, l)
-      WM_STAGE(ST_CROSS_COMBINE, l)
-      WM_STAGE(ST_CROSS_O, l)
-      WM_STAGE(ST_FC1, l)
-      WM_STAGE(ST_FC2, l)
-      WM_STAGE(ST_HEADS, 0)
-    }
-  } else {
-    WM_STAGE(ST_HEADS, 0)
-  }
-  WM_STAGE(ST_VOCAB, 0)
-  WM_STAGE(ST_SELECT, 0)
-  if (mode == 1) {
-    WM_STAGE(ST_ACCEPT, 0)
-  }
-#undef WM_STAGE
-}
-
 __global__ void __launch_bounds__(WM_DEC_THREADS, 1)
 dec_iteration_kernel(const DecModel* __restrict__ m) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  if (m->st->done) return;   // uniform: `done` only changes in the last stage of an iteration
-  // bar[0] = arrival counter, bar[1] = released epoch, bar[2] = epoch at kernel entry.  bar[2]
-  // is only rewritten after the last barrier of a launch, i.e. after every CTA has read it.
+  extern __shared__ __align__(128) unsigned char smem[];
+  const DecState* st = m->st;
+  if (st->done) return;   // uniform: `done` / `need_a` only change in the last stage of an iteration
+  const int need_a = st->need_a;
+  // bar[2] = barrier epoch at kernel entry; only rewritten after the last barrier of a launch,
+  // i.e. after every CTA has read it.
   unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(&m->bar[2]);
-  run_pass(m, 0, blockIdx.x, gridDim.x, smem, epoch);
-  run_pass(m, 1, blockIdx.x, gridDim.x, smem, epoch);
+  unsigned int* bar = m->bar;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  auto run = [&](int stage, int mode, int layer) {
+    run_stage(m, stage, mode, layer, cta, ncta, smem);
+    grid_barrier(bar, epoch, ncta);
+  };
+  if (need_a) seq_sweep(m->n_layers, m->has_block, MODE_A, run);
+  seq_tail(m->n_layers, m->has_block, run);
+  seq_verify(m->n_layers, m->has_block, run);
   if (blockIdx.x == 0 && threadIdx.x == 0) m->bar[2] = epoch;
 }
+
+#include "decode_ring.cuh"
 
 // -----------------------------------------------------------------------------------------
 // host-side launchers
 // -----------------------------------------------------------------------------------------
+// Flattened stage program {stage, mode, layer} x n, lists: [off0,off1) sweep A, [off1,off2) tail,
+// [off2,off3) verify -- what the ring kernel (consumer and producer side) walks.
+void dec_build_program(int n_layers, int has_block, std::vector<int>& flat, int off[4]) {
+  flat.clear();
+  auto push = [&](int stage, int mode, int layer) { flat.push_back(stage); flat.push_back(mode); flat.push_back(layer); };
+  off[0] = 0;
+  seq_sweep(n_layers, has_block, MODE_A, push);
+  off[1] = (int)flat.size() / 3;
+  seq_tail(n_layers, has_block, push);
+  off[2] = (int)flat.size() / 3;
+  seq_verify(n_layers, has_block, push);
+  off[3] = (int)flat.size() / 3;
+}
+
+size_t dec_ring_smem_bytes(int d) { return ring_smem_bytes(d); }
+
+cudaError_t dec_launch_iteration_ring(const DecModel* dm, const DecHostInfo& hi, cudaStream_t s) {
+  void* args[] = {(void*)&dm};
+  return cudaLaunchCooperativeKernel((void*)dec_iteration_ring_kernel, dim3(hi.n_sm), dim3(WM_DEC_THREADS), args,
+                                     hi.smem_ring, s);
+}
+
 size_t dec_smem_bytes(int d, int ffn) {
   size_t s = gemm_smem_bytes(d);
   size_t s2 = gemm_smem_bytes(ffn);
@@ -866,10 +931,12 @@ size_t dec_smem_bytes(int d, int ffn) {
   return s;
 }
 
-cudaError_t dec_configure(size_t smem) {
+cudaError_t dec_configure(size_t smem, size_t smem_ring) {
   cudaError_t e = cudaFuncSetAttribute(dec_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dec_iteration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(dec_iteration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dec_iteration_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring);
 }
 
 static int stage_grid(int stage, int T, int n_sm, int H, int K) {
@@ -877,39 +944,29 @@ static int stage_grid(int stage, int T, int n_sm, int H, int K) {
     case ST_EMBED: return T;
     case ST_SELF_ATTN: return H * T;
     case ST_CROSS_ATTN: return H * WM_CROSS_CHUNKS;
-    case ST_CROSS_COMBINE: return 8;
     case ST_FINAL_LN: return 1;
     case ST_COPY_HIDDEN: return 8;
+    case ST_TAIL_SEED: return 2;
     case ST_SELECT: return K + 1;
     case ST_ACCEPT: return 1;
     default: return n_sm;
   }
 }
 
-// Enqueue one pass as individual stage kernels (captured into a graph by the caller).
-cudaError_t dec_enqueue_pass(const DecModel* dm, const DecHostInfo& hi, int mode, int T, cudaStream_t s, int64_t* n_launch) {
-  auto launch = [&](int stage, int layer) {
-    int grid = stage_grid(stage, T, hi.n_sm, hi.H, hi.K);
-    dec_stage_kernel<<<grid, WM_DEC_THREADS, hi.smem, s>>>(dm, stage, mode, layer);
+// Enqueue one phase as individual stage kernels (captured into a graph by the caller).
+//   PH_SWEEP_A: sweep over T uncached rows (kernels return at once unless state.need_a)
+//   PH_TAIL   : candidates from the carried hidden state
+//   PH_VERIFY : sweep B + acceptance
+cudaError_t dec_enqueue_phase(const DecModel* dm, const DecHostInfo& hi, int phase, int T, cudaStream_t s, int64_t* n_launch) {
+  auto launch = [&](int stage, int mode, int layer) {
+    const int rows = (mode == MODE_B) ? hi.K + 1 : (mode == MODE_TAIL ? 1 : T);
+    const int grid = stage_grid(stage, rows, hi.n_sm, hi.H, hi.K);
+    dec_stage_kernel<<<grid, WM_DEC_THREADS, hi.smem, s>>>(dm, stage, mode, layer, phase);
     if (n_launch) ++*n_launch;
   };
-  launch(ST_EMBED, 0);
-  auto layer_full = [&](int l) {
-    launch(ST_QKV, l); launch(ST_SELF_ATTN, l); launch(ST_OPROJ, l); launch(ST_CROSS_Q, l);
-    launch(ST_CROSS_ATTN, l); launch(ST_CROSS_COMBINE, l); launch(ST_CROSS_O, l); launch(ST_FC1, l); launch(ST_FC2, l);
-  };
-  for (int l = 0; l < hi.n_layers; ++l) layer_full(l);
-  launch(ST_FINAL_LN, 0);
-  if (hi.has_block) {
-    launch(ST_COPY_HIDDEN, 0);
-    if (mode == 0) { layer_full(hi.n_layers); launch(ST_HEADS, 0); }
-    else launch(ST_QKV, hi.n_layers);
-  } else {
-    launch(ST_HEADS, 0);
-  }
-  launch(ST_VOCAB, 0);
-  launch(ST_SELECT, 0);
-  if (mode == 1) launch(ST_ACCEPT, 0);
+  if (phase == PH_SWEEP_A) seq_sweep(hi.n_layers, hi.has_block, MODE_A, launch);
+  else if (phase == PH_TAIL) seq_tail(hi.n_layers, hi.has_block, launch);
+  else seq_verify(hi.n_layers, hi.has_block, launch);
   return cudaGetLastError();
 }
 

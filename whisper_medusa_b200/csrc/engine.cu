@@ -60,11 +60,12 @@ struct wm_handle {
   uint8_t* tok_mask = nullptr;
   float* pen_tab = nullptr;
   unsigned int* bar = nullptr;
+  int* prog = nullptr;
   DecHostInfo hi;
-  std::map<int, cudaGraphExec_t> graph_a;  // keyed by T
-  cudaGraphExec_t graph_b = nullptr;
+  std::map<int, cudaGraphExec_t> graph_a;  // sweep A, keyed by T
+  cudaGraphExec_t graph_tail = nullptr, graph_b = nullptr;
   int64_t launches_a[WM_MAX_T + 1] = {0};
-  int64_t launches_b = 0;
+  int64_t launches_tail = 0, launches_b = 0;
   int decode_mode = 0;
   bool encoded = false;
   // pinned staging + timing
@@ -260,7 +261,9 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   CK(dalloc(&m.ffn_h, (size_t)WM_MAX_T * f));
   CK(dalloc(&m.hidden, (size_t)WM_MAX_T * d));
   CK(dalloc(&m.head_h, (size_t)WM_MAX_T * d));
+  CK(dalloc(&m.carry, d));
   CK(dalloc(&m.cross_part, (size_t)c.n_heads * WM_CROSS_CHUNKS * WM_MAX_T * (WM_HEAD_DIM + 2)));
+  CK(dalloc(&m.cross_cnt, (size_t)c.n_heads));
   CK(dalloc(&m.logits_a, (size_t)WM_MAX_T * V));
   CK(dalloc(&m.logits_b, (size_t)WM_MAX_T * V));
   CK(dalloc(&h->st, 1));
@@ -275,7 +278,15 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   h->hi.n_sm = h->n_sm; h->hi.H = c.n_heads; h->hi.K = c.medusa_num_heads; h->hi.n_layers = c.dec_layers;
   h->hi.has_block = m.has_block;
   h->hi.smem = dec_smem_bytes((int)d, (int)f);
-  CK(dec_configure(h->hi.smem));
+  h->hi.smem_ring = dec_ring_smem_bytes((int)d);
+  CK(dec_configure(h->hi.smem, h->hi.smem_ring));
+  {
+    std::vector<int> flat;
+    dec_build_program(c.dec_layers, m.has_block, flat, m.prog_off);
+    CK(dalloc(&h->prog, flat.size()));
+    CK(cudaMemcpy(h->prog, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+    m.prog = reinterpret_cast<const StageInstr*>(h->prog);
+  }
   CK(enc_gemm_configure());
   // the skinny-GEMM work split assumes at most WM_MAXR(3) 16-row units per warp
   {
@@ -292,14 +303,15 @@ extern "C" int wm_destroy(wm_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& kv : h->graph_a) cudaGraphExecDestroy(kv.second);
   if (h->graph_b) cudaGraphExecDestroy(h->graph_b);
+  if (h->graph_tail) cudaGraphExecDestroy(h->graph_tail);
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(h->pcm); F(h->mel32); F(h->melfb); F(h->gmax); F(h->x_tm); F(h->h1); F(h->x32); F(h->enc32); F(h->ln16);
   F(h->qkv16); F(h->att16); F(h->ffn16); F(h->enc16);
   for (auto p : h->cross_kv) F(p);
   for (auto p : h->self_k) F(p);
   for (auto p : h->self_v) F(p);
-  F(h->hm.x); F(h->hm.q); F(h->hm.attn); F(h->hm.ffn_h); F(h->hm.hidden); F(h->hm.head_h); F(h->hm.cross_part);
-  F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->dm);
+  F(h->hm.x); F(h->hm.q); F(h->hm.attn); F(h->hm.ffn_h); F(h->hm.hidden); F(h->hm.head_h); F(h->hm.carry); F(h->hm.cross_part); F(h->hm.cross_cnt);
+  F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->prog); F(h->dm);
   if (h->wowned) F(h->wdev);
   if (h->h_state) cudaFreeHost(h->h_state);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -505,23 +517,25 @@ extern "C" int wm_encode_mel(wm_handle* h, const float* mel) {
 // ---------------------------------------------------------------------------------------------
 // decode loop
 // ---------------------------------------------------------------------------------------------
-static int get_graph(wm_handle* h, int mode, int T, cudaGraphExec_t* out, int64_t* n_launch) {
-  if (mode == 1 && h->graph_b) { *out = h->graph_b; *n_launch = h->launches_b; return WM_OK; }
-  if (mode == 0) {
+static int get_graph(wm_handle* h, int phase, int T, cudaGraphExec_t* out, int64_t* n_launch) {
+  if (phase == 2 && h->graph_b) { *out = h->graph_b; *n_launch = h->launches_b; return WM_OK; }
+  if (phase == 1 && h->graph_tail) { *out = h->graph_tail; *n_launch = h->launches_tail; return WM_OK; }
+  if (phase == 0) {
     auto it = h->graph_a.find(T);
     if (it != h->graph_a.end()) { *out = it->second; *n_launch = h->launches_a[T]; return WM_OK; }
   }
   cudaGraph_t g;
   int64_t nl = 0;
   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-  cudaError_t e = dec_enqueue_pass(h->dm, h->hi, mode, T, h->stream, &nl);
+  cudaError_t e = dec_enqueue_phase(h->dm, h->hi, phase, T, h->stream, &nl);
   cudaError_t e2 = cudaStreamEndCapture(h->stream, &g);
   CK(e);
   CK(e2);
   cudaGraphExec_t ge;
   CK(cudaGraphInstantiate(&ge, g, 0));
   CK(cudaGraphDestroy(g));
-  if (mode == 1) { h->graph_b = ge; h->launches_b = nl; }
+  if (phase == 2) { h->graph_b = ge; h->launches_b = nl; }
+  else if (phase == 1) { h->graph_tail = ge; h->launches_tail = nl; }
   else { h->graph_a[T] = ge; h->launches_a[T] = nl; }
   *out = ge; *n_launch = nl;
   return WM_OK;
@@ -557,7 +571,7 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
   {
     static thread_local DecState hs;
     memset(&hs, 0, sizeof hs);
-    hs.L = n_prompt; hs.kv_len = 0; hs.done = 0; hs.n_iter = 0; hs.max_iters = gp->max_iters;
+    hs.L = n_prompt; hs.kv_len = 0; hs.done = 0; hs.n_iter = 0; hs.max_iters = gp->max_iters; hs.need_a = 1;
     hs.max_length = gp->max_length; hs.eos = gp->eos_token_id; hs.pad = gp->pad_token_id;
     hs.begin_index = gp->begin_index; hs.temperature = gp->temperature; hs.post_thr = gp->posterior_threshold;
     hs.post_alpha = gp->posterior_alpha;
@@ -566,15 +580,17 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
     // loop always runs at least once (model.py:635).
     CK(cudaMemcpyAsync(h->st, &hs, sizeof hs, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(h->bar, 0, 8 * sizeof(unsigned int), s));
+    CK(cudaMemsetAsync(h->hm.cross_cnt, 0, (size_t)h->cfg.n_heads * sizeof(unsigned int), s));
     CK(cudaStreamSynchronize(s));
   }
-  cudaGraphExec_t gA1 = nullptr, gAp = nullptr, gB = nullptr;
-  int64_t nA1 = 0, nAp = 0, nB = 0;
+  cudaGraphExec_t gA1 = nullptr, gAp = nullptr, gT = nullptr, gB = nullptr;
+  int64_t nA1 = 0, nAp = 0, nT = 0, nB = 0;
   if (h->decode_mode == 0) {
     int r;
     if ((r = get_graph(h, 0, n_prompt, &gAp, &nAp)) != WM_OK) return r;
     if ((r = get_graph(h, 0, 1, &gA1, &nA1)) != WM_OK) return r;
-    if ((r = get_graph(h, 1, K + 1, &gB, &nB)) != WM_OK) return r;
+    if ((r = get_graph(h, 1, 1, &gT, &nT)) != WM_OK) return r;
+    if ((r = get_graph(h, 2, K + 1, &gB, &nB)) != WM_OK) return r;
   }
   CK(cudaEventRecord(h->ev[3], s));
   int L = n_prompt, iters = 0, done = 0;
@@ -589,11 +605,16 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
     for (int i = 0; i < lb; ++i) {
       if (h->decode_mode == 0) {
         const bool first = (iters + i == 0);
+        // sweep A kernels return immediately unless the state says the newest token is uncached
         CK(cudaGraphLaunch(first ? gAp : gA1, s));
+        CK(cudaGraphLaunch(gT, s));
         CK(cudaGraphLaunch(gB, s));
-        h->launches[2] += (first ? nAp : nA1) + nB;
-      } else {
+        h->launches[2] += (first ? nAp : nA1) + nT + nB;
+      } else if (h->decode_mode == 1) {
         CK(dec_launch_iteration(h->dm, h->hi, s));
+        h->launches[2] += 1;
+      } else {
+        CK(dec_launch_iteration_ring(h->dm, h->hi, s));
         h->launches[2] += 1;
       }
     }
@@ -660,6 +681,6 @@ extern "C" int64_t wm_last_launches(wm_handle* h, int32_t what) {
 extern "C" int wm_set_decode_mode(wm_handle* h, int32_t mode) {
   if (!h) return WM_ERR_INVALID;
   int prev = h->decode_mode;
-  if (mode == 0 || mode == 1) h->decode_mode = mode;
+  if (mode >= 0 && mode <= 2) h->decode_mode = mode;
   return prev;
 }

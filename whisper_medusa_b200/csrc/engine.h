@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace wm {
 
 struct DecModel;
@@ -12,12 +14,17 @@ struct DecHostInfo {
   int n_sm;
   int H, K, n_layers, has_block;
   size_t smem;
+  size_t smem_ring;
 };
 
 // ---- decode.cu ----
 size_t dec_smem_bytes(int d, int ffn);
-cudaError_t dec_configure(size_t smem);
-cudaError_t dec_enqueue_pass(const DecModel* dm, const DecHostInfo& hi, int mode, int T, cudaStream_t s, int64_t* n_launch);
+cudaError_t dec_configure(size_t smem, size_t smem_ring);
+size_t dec_ring_smem_bytes(int d);
+void dec_build_program(int n_layers, int has_block, std::vector<int>& flat, int off[4]);
+cudaError_t dec_launch_iteration_ring(const DecModel* dm, const DecHostInfo& hi, cudaStream_t s);
+// phase: 0 = sweep A over T uncached rows, 1 = tail (candidates), 2 = verify sweep + accept
+cudaError_t dec_enqueue_phase(const DecModel* dm, const DecHostInfo& hi, int phase, int T, cudaStream_t s, int64_t* n_launch);
 cudaError_t dec_launch_iteration(const DecModel* dm, const DecHostInfo& hi, cudaStream_t s);
 
 // ---- mel.cu ----

@@ -195,10 +195,11 @@ class WhisperMedusaModel:
             pass
 
     def set_decode_mode(self, mode: str) -> None:
-        """``"graph"``: one CUDA graph of stage kernels per pass; ``"persistent"``: one cooperative
-        kernel per speculative iteration."""
+        """``"graph"``: CUDA graphs of stage kernels (debug / per-stage profiling); ``"persistent"``: one
+        cooperative kernel per speculative iteration with the weight ring (product path);
+        ``"persistent_simple"``: the same without the ring (grid barriers only)."""
         self._require_engine()
-        _lib.load().wm_set_decode_mode(self._handle, {"graph": 0, "persistent": 1}[mode])
+        _lib.load().wm_set_decode_mode(self._handle, {"graph": 0, "persistent_simple": 1, "persistent": 2}[mode])
 
     def _require_engine(self):
         if self._handle is None:
