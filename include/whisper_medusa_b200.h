@@ -120,6 +120,13 @@ int64_t wm_last_launches(wm_handle* h, int32_t what);
  * the shared-memory weight ring (bulk-async prefetch across barriers; the product path).
  * Returns the previous mode. */
 int wm_set_decode_mode(wm_handle* h, int32_t mode);
+/* Engine options: "decode_mode" (as above); "enc_gemm" 0 = mma.sync encoder GEMM, 1 = tcgen05/TMA/TMEM
+ * encoder GEMM. */
+int wm_set_option(wm_handle* h, const char* key, int32_t value);
+/* Debug: per-stage timeline of the last persistent iteration (after wm_set_option(h, "profile", 1)).
+ * Rows of 7 int64: stage id, mode, layer, body ns and barrier-wait ns seen by CTA 0, then by the
+ * last CTA. */
+int wm_get_stage_profile(wm_handle* h, int64_t* out, int32_t cap_rows, int32_t* n_rows);
 
 #ifdef __cplusplus
 }

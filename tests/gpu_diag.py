@@ -23,6 +23,7 @@ from whisper_medusa_b200 import WhisperMedusaModel  # noqa: E402
 from whisper_medusa_b200.synthetic import preset_config, synthetic_audio, synthetic_state_dict  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+TC = "--tc" in sys.argv
 
 
 def first_diff(a, b):
@@ -44,6 +45,8 @@ def run_case(name: str, mode: str, use_oracle: bool = True):
     pen = None if g["penalty"][0] < 0 else (int(g["penalty"][0]), float(g["penalty"][1]))
     model = WhisperMedusaModel(cfg, sd).to("cuda:0")
     model.set_decode_mode(mode)
+    if TC:
+        model.set_option("enc_gemm", 1)   # tcgen05 / TMA / TMEM encoder GEMM
     print(f"[{name}/{mode}] setup {time.time() - t0:.1f}s", flush=True)
     language = "en" if cfg.is_multilingual else None
     kw = dict(language=language, max_length=max_len, exponential_decay_length_penalty=pen, medusa_temperature=temp)
@@ -93,10 +96,13 @@ def run_case(name: str, mode: str, use_oracle: bool = True):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    argv = sys.argv[1:]
     mode = "graph"
-    if "--mode" in sys.argv:
-        mode = sys.argv[sys.argv.index("--mode") + 1]
+    if "--mode" in argv:
+        i = argv.index("--mode")
+        mode = argv[i + 1]
+        del argv[i:i + 2]
+    args = [a for a in argv if not a.startswith("--")]
     names = args or ["micro_linear_k4", "micro_block_k10", "micro_linear_k4_t0", "tiny_linear_k4", "tiny_block_k4"]
     ok = True
     for n in names:

@@ -154,6 +154,7 @@ struct DecModel {
   int prog_off[4];
   DecState* st;
   unsigned int* bar;  // grid-barrier words for the persistent kernel
+  unsigned long long* prof;  // optional stage timeline [2 CTAs][n_instr][3] (ns), null = off
 };
 
 }  // namespace wm

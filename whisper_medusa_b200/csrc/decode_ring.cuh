@@ -46,6 +46,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ bool is_gemm_stage(int st) {
   return st == ST_QKV || st == ST_OPROJ || st == ST_CROSS_Q || st == ST_CROSS_O || st == ST_FC1 || st == ST_FC2 ||
          st == ST_HEADS || st == ST_VOCAB;
@@ -383,6 +389,10 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ m) {
     const int i0 = m->prog_off[list], i1 = m->prog_off[list + 1];
     for (int ip = i0; ip < i1; ++ip) {
       const StageInstr in = m->prog[ip];
+      // optional per-stage timeline (CTA 0 and the last CTA): begin / end of body / end of barrier
+      const bool prof = m->prof != nullptr && threadIdx.x == 0 && (cta == 0 || cta == ncta - 1);
+      unsigned long long* pr = prof ? m->prof + ((size_t)(cta == 0 ? 0 : 1) * m->prog_off[3] + ip) * 3 : nullptr;
+      if (prof) pr[0] = global_timer_ns();
       if (is_gemm_stage(in.stage)) {
         GemmDesc g = make_gemm_desc(m, in.stage, in.mode, in.layer);
         stage_gemm_ring(rc, g, xhi, xlo, partial, rows_dirty);
@@ -391,7 +401,9 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ m) {
         // attention stages overlay the activation slice: everything there is dirty now
         if (in.stage == ST_SELF_ATTN || in.stage == ST_CROSS_ATTN || in.stage == ST_SELECT) rows_dirty = 16;
       }
+      if (prof) pr[1] = global_timer_ns();
       grid_barrier(bar, epoch, ncta);
+      if (prof) pr[2] = global_timer_ns();
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) m->bar[2] = epoch;

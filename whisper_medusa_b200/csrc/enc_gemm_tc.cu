@@ -1,0 +1,315 @@
+// Encoder-side dense GEMM on the 5th-generation tensor cores (sm_100a):
+//   C[M,N] = A[M,K] * W[N,K]^T   fp16 operands (both K-major), fp32 accumulation in TMEM.
+//
+// Structure (one 128x128 output tile per CTA, K swept in 64-column blocks):
+//   warp 0  : TMA producer   -- cp.async.bulk.tensor.2d (SWIZZLE_128B) of the A and W tiles into a
+//                               6-stage shared-memory ring, completion on `full` mbarriers
+//   warp 1  : MMA issuer     -- one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//                               (M=128, N=128, K=16) x4 per stage, accumulator = 128 TMEM columns;
+//                               tcgen05.commit releases the stage (`empty`) / signals the epilogue
+//   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns per instruction) -> registers ->
+//                               bias / GELU / residual / position epilogue -> global
+// The A operand may be an "implicit im2col" view: conv1/conv2 read a time-major activation whose
+// GEMM rows overlap (row stride 80 resp. 2d elements) -- the TMA tensor map simply carries that
+// stride, no im2col buffer exists.
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
+#include "common.cuh"
+#include "engine.h"
+
+namespace wm {
+
+#define TC_BM 128
+#define TC_BN 128
+#define TC_BK 64
+#define TC_STAGES 6
+#define TC_THREADS 192
+#define TC_TMEM_COLS 128
+#define TC_STAGE_BYTES ((TC_BM + TC_BN) * TC_BK * 2)
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tc_tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute UMMA::SmemDescriptor, sm_100):
+//   [0,14) start address >> 4 | [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B) |
+//   [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor (cute UMMA::InstrDescriptor): c_format F32 (bit 4), a/b F16 (0),
+// both K-major (bits 15,16 = 0), n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29)
+__device__ __forceinline__ constexpr uint32_t tc_instr_desc() {
+  return (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+      "[%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcArgs {
+  int M, N, K;
+  int epi;
+  const float* bias;
+  __half* out16; int ldo16;
+  float* out32; int ldo32;
+  const float* pos;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // stage s: A tile [128 rows][64 halfs] at s*32K, W tile at s*32K + 16K (both 1024-B aligned, SW128)
+  __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tmem_full;
+  __shared__ uint32_t s_tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int KT = a.K / TC_BK;
+  const uint32_t smem_base = tc_smem_u32(smem_raw);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) {
+      tc_mbar_init(tc_smem_u32(&s_full[s]), 1);
+      tc_mbar_init(tc_smem_u32(&s_empty[s]), 1);
+    }
+    tc_mbar_init(tc_smem_u32(&s_tmem_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem_base)),
+                 "n"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % TC_STAGES;
+        const uint32_t ph = (kt / TC_STAGES) & 1;
+        tc_mbar_wait(tc_smem_u32(&s_empty[s]), ph ^ 1);
+        const uint32_t full = tc_smem_u32(&s_full[s]);
+        tc_mbar_expect_tx(full, TC_STAGE_BYTES);
+        tc_tma_load_2d(smem_base + s * TC_STAGE_BYTES, &map_a, kt * TC_BK, m0, full);
+        tc_tma_load_2d(smem_base + s * TC_STAGE_BYTES + TC_BM * TC_BK * 2, &map_w, kt * TC_BK, n0, full);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = tc_instr_desc();
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % TC_STAGES;
+        const uint32_t ph = (kt / TC_STAGES) & 1;
+        tc_mbar_wait(tc_smem_u32(&s_full[s]), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t adesc = tc_smem_desc(smem_base + s * TC_STAGE_BYTES);
+        const uint64_t bdesc = tc_smem_desc(smem_base + s * TC_STAGE_BYTES + TC_BM * TC_BK * 2);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // advance 16 halfs = 32 B inside the 128-B swizzle atom: +2 in the (>>4) start address
+          tc_mma(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kt > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(tc_smem_u32(&s_empty[s]));      // stage reusable once these MMAs have read it
+      }
+      tc_commit(tc_smem_u32(&s_tmem_full));       // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    const int q = warp & 3;
+    tc_mbar_wait(tc_smem_u32(&s_tmem_full), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < a.M;
+#pragma unroll 1
+    for (int cb = 0; cb < TC_BN / 32; ++cb) {
+      uint32_t v[32];
+      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
+      if (!row_ok) continue;
+      const int col0 = n0 + cb * 32;
+      if (EPI == ENC_EPI_BIAS_F16 || EPI == ENC_EPI_BIAS_GELU_F16) {
+        __half* dst = a.out16 + (size_t)row * a.ldo16 + col0;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x0 = __uint_as_float(v[c8 * 8 + 2 * e]) + a.bias[col0 + c8 * 8 + 2 * e];
+            float x1 = __uint_as_float(v[c8 * 8 + 2 * e + 1]) + a.bias[col0 + c8 * 8 + 2 * e + 1];
+            if (EPI == ENC_EPI_BIAS_GELU_F16) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); }
+            pk[e] = pack_half2(x0, x1);
+          }
+          *reinterpret_cast<uint4*>(dst + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      } else {
+        float* dst = a.out32 + (size_t)row * a.ldo32 + col0;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 o;
+          float x0 = __uint_as_float(v[c4 * 4 + 0]) + a.bias[col0 + c4 * 4 + 0];
+          float x1 = __uint_as_float(v[c4 * 4 + 1]) + a.bias[col0 + c4 * 4 + 1];
+          float x2 = __uint_as_float(v[c4 * 4 + 2]) + a.bias[col0 + c4 * 4 + 2];
+          float x3 = __uint_as_float(v[c4 * 4 + 3]) + a.bias[col0 + c4 * 4 + 3];
+          if (EPI == ENC_EPI_BIAS_RES_F32) {
+            const float4 r = *reinterpret_cast<const float4*>(dst + c4 * 4);
+            o = make_float4(r.x + x0, r.y + x1, r.z + x2, r.w + x3);
+          } else {
+            const float4 pz = *reinterpret_cast<const float4*>(a.pos + (size_t)row * a.N + col0 + c4 * 4);
+            o = make_float4(gelu_erf(x0) + pz.x, gelu_erf(x1) + pz.y, gelu_erf(x2) + pz.z, gelu_erf(x3) + pz.w);
+          }
+          *reinterpret_cast<float4*>(dst + c4 * 4) = o;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps (cached per operand view) and launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp16 view [rows][K] with row stride `ld` elements, boxes of [128 rows][64 columns], SWIZZLE_128B
+static bool make_map(CUtensorMap* map, const __half* base, uint64_t rows, uint64_t K, uint64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {K, rows};
+  cuuint64_t strides[1] = {ld * sizeof(__half)};
+  cuuint32_t box[2] = {TC_BK, TC_BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static const size_t kTcSmem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
+
+cudaError_t enc_gemm_tc_configure() {
+  cudaError_t e;
+#define WM_SET(EPI)                                                                                              \
+  e = cudaFuncSetAttribute(enc_gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem); \
+  if (e != cudaSuccess) return e;
+  WM_SET(ENC_EPI_BIAS_F16)
+  WM_SET(ENC_EPI_BIAS_GELU_F16)
+  WM_SET(ENC_EPI_BIAS_RES_F32)
+  WM_SET(ENC_EPI_BIAS_GELU_POS_F32)
+#undef WM_SET
+  return get_encode_fn() ? cudaSuccess : cudaErrorNotSupported;
+}
+
+// `a_rows` = rows of the A view that may be touched (the allocation is padded accordingly)
+cudaError_t enc_gemm_tc(const EncGemmArgs& g, int a_rows, cudaStream_t s, int64_t* n_launch) {
+  if (g.N % TC_BN != 0 || g.K % TC_BK != 0 || (g.lda % 8) != 0) return cudaErrorInvalidValue;
+  typedef std::tuple<const void*, uint64_t, uint64_t, uint64_t> Key;
+  static thread_local std::map<Key, CUtensorMap> cache;
+  auto get = [&](const __half* base, uint64_t rows, uint64_t K, uint64_t ld, CUtensorMap* out) -> bool {
+    Key k(base, rows, K, ld);
+    auto it = cache.find(k);
+    if (it == cache.end()) {
+      CUtensorMap m;
+      if (!make_map(&m, base, rows, K, ld)) return false;
+      it = cache.emplace(k, m).first;
+    }
+    *out = it->second;
+    return true;
+  };
+  CUtensorMap ma, mw;
+  if (!get(g.A, (uint64_t)a_rows, (uint64_t)g.K, (uint64_t)g.lda, &ma)) return cudaErrorInvalidValue;
+  if (!get(g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.K, &mw)) return cudaErrorInvalidValue;
+  TcArgs a;
+  a.M = g.M; a.N = g.N; a.K = g.K; a.epi = g.epi; a.bias = g.bias; a.out16 = g.out16; a.ldo16 = g.ldo16;
+  a.out32 = g.out32; a.ldo32 = g.ldo32; a.pos = g.pos;
+  dim3 grid(g.N / TC_BN, (g.M + TC_BM - 1) / TC_BM);
+  switch (g.epi) {
+    case ENC_EPI_BIAS_F16: enc_gemm_tc_kernel<ENC_EPI_BIAS_F16><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a); break;
+    case ENC_EPI_BIAS_GELU_F16: enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_F16><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a); break;
+    case ENC_EPI_BIAS_RES_F32: enc_gemm_tc_kernel<ENC_EPI_BIAS_RES_F32><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a); break;
+    case ENC_EPI_BIAS_GELU_POS_F32: enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_POS_F32><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  if (n_launch) ++*n_launch;
+  return cudaGetLastError();
+}
+
+}  // namespace wm

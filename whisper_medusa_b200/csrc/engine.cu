@@ -61,12 +61,15 @@ struct wm_handle {
   float* pen_tab = nullptr;
   unsigned int* bar = nullptr;
   int* prog = nullptr;
+  unsigned long long* prof = nullptr;
   DecHostInfo hi;
   std::map<int, cudaGraphExec_t> graph_a;  // sweep A, keyed by T
   cudaGraphExec_t graph_tail = nullptr, graph_b = nullptr;
   int64_t launches_a[WM_MAX_T + 1] = {0};
   int64_t launches_tail = 0, launches_b = 0;
   int decode_mode = 0;
+  int enc_gemm_impl = 0;   // 0 = mma.sync kernel, 1 = tcgen05/TMA kernel
+  bool tc_ok = false;
   bool encoded = false;
   // pinned staging + timing
   int* h_state = nullptr;  // pinned copy of the DecState header
@@ -288,6 +291,8 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
     m.prog = reinterpret_cast<const StageInstr*>(h->prog);
   }
   CK(enc_gemm_configure());
+  h->tc_ok = (enc_gemm_tc_configure() == cudaSuccess);
+  (void)cudaGetLastError();
   // the skinny-GEMM work split assumes at most WM_MAXR(3) 16-row units per warp
   {
     const int rows = (int)((V + h->n_sm - 1) / h->n_sm);
@@ -311,7 +316,7 @@ extern "C" int wm_destroy(wm_handle* h) {
   for (auto p : h->self_k) F(p);
   for (auto p : h->self_v) F(p);
   F(h->hm.x); F(h->hm.q); F(h->hm.attn); F(h->hm.ffn_h); F(h->hm.hidden); F(h->hm.head_h); F(h->hm.carry); F(h->hm.cross_part); F(h->hm.cross_cnt);
-  F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->prog); F(h->dm);
+  F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->prog); F(h->prof); F(h->dm);
   if (h->wowned) F(h->wdev);
   if (h->h_state) cudaFreeHost(h->h_state);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -420,6 +425,11 @@ extern "C" int wm_set_suppress(wm_handle* h, const int32_t* sup, int32_t n_sup, 
 // ---------------------------------------------------------------------------------------------
 // frontend + encoder
 // ---------------------------------------------------------------------------------------------
+static cudaError_t gemm_dispatch(wm_handle* h, const EncGemmArgs& a, cudaStream_t s, int64_t* nl) {
+  if (h->enc_gemm_impl == 1) return enc_gemm_tc(a, (int)align_up((size_t)a.M, 128), s, nl);
+  return enc_gemm(a, s, nl);
+}
+
 static int run_encoder(wm_handle* h) {
   const wm_config& c = h->cfg;
   const int d = c.d_model, f = c.ffn_dim, S = h->S;
@@ -430,34 +440,34 @@ static int run_encoder(wm_handle* h) {
   // conv1 (k=3, pad 1) as an implicit GEMM over the time-major mel: row t = frames t-1..t+1
   a.A = h->x_tm; a.lda = 80; a.W = wptr<__half>(h, "enc.conv1_w"); a.bias = wptr<float>(h, "enc.conv1_b");
   a.M = kFrames; a.N = d; a.K = 256; a.epi = ENC_EPI_BIAS_GELU_F16; a.out16 = h->h1 + d; a.ldo16 = d;
-  CK(enc_gemm(a, s, nl));
+  CK(gemm_dispatch(h, a, s, nl));
   // conv2 (k=3, stride 2, pad 1): row t = h1 rows 2t..2t+2 ; + GELU + sinusoid positions
   memset(&a, 0, sizeof a);
   a.A = h->h1; a.lda = 2 * d; a.W = wptr<__half>(h, "enc.conv2_w"); a.bias = wptr<float>(h, "enc.conv2_b");
   a.M = S; a.N = d; a.K = 3 * d; a.epi = ENC_EPI_BIAS_GELU_POS_F32; a.out32 = h->x32; a.ldo32 = d;
   a.pos = wptr<float>(h, "enc.pos");
-  CK(enc_gemm(a, s, nl));
+  CK(gemm_dispatch(h, a, s, nl));
   for (int i = 0; i < c.enc_layers; ++i) {
     std::string p = "enc." + std::to_string(i) + ".";
     CK(enc_layernorm(h->x32, wptr<float>(h, p + "ln1_g"), wptr<float>(h, p + "ln1_b"), h->ln16, nullptr, S, d, s, nl));
     memset(&a, 0, sizeof a);
     a.A = h->ln16; a.lda = d; a.W = wptr<__half>(h, p + "qkv_w"); a.bias = wptr<float>(h, p + "qkv_b");
     a.M = S; a.N = 3 * d; a.K = d; a.epi = ENC_EPI_BIAS_F16; a.out16 = h->qkv16; a.ldo16 = 3 * d;
-    CK(enc_gemm(a, s, nl));
+    CK(gemm_dispatch(h, a, s, nl));
     CK(enc_attention(h->qkv16, h->att16, S, d, c.n_heads, s, nl));
     memset(&a, 0, sizeof a);
     a.A = h->att16; a.lda = d; a.W = wptr<__half>(h, p + "o_w"); a.bias = wptr<float>(h, p + "o_b");
     a.M = S; a.N = d; a.K = d; a.epi = ENC_EPI_BIAS_RES_F32; a.out32 = h->x32; a.ldo32 = d;
-    CK(enc_gemm(a, s, nl));
+    CK(gemm_dispatch(h, a, s, nl));
     CK(enc_layernorm(h->x32, wptr<float>(h, p + "ln2_g"), wptr<float>(h, p + "ln2_b"), h->ln16, nullptr, S, d, s, nl));
     memset(&a, 0, sizeof a);
     a.A = h->ln16; a.lda = d; a.W = wptr<__half>(h, p + "fc1_w"); a.bias = wptr<float>(h, p + "fc1_b");
     a.M = S; a.N = f; a.K = d; a.epi = ENC_EPI_BIAS_GELU_F16; a.out16 = h->ffn16; a.ldo16 = f;
-    CK(enc_gemm(a, s, nl));
+    CK(gemm_dispatch(h, a, s, nl));
     memset(&a, 0, sizeof a);
     a.A = h->ffn16; a.lda = f; a.W = wptr<__half>(h, p + "fc2_w"); a.bias = wptr<float>(h, p + "fc2_b");
     a.M = S; a.N = d; a.K = f; a.epi = ENC_EPI_BIAS_RES_F32; a.out32 = h->x32; a.ldo32 = d;
-    CK(enc_gemm(a, s, nl));
+    CK(gemm_dispatch(h, a, s, nl));
   }
   CK(enc_layernorm(h->x32, wptr<float>(h, "enc.lnf_g"), wptr<float>(h, "enc.lnf_b"), h->enc16, h->enc32, S, d, s, nl));
   // cross-attention K/V of every decoder layer, written in the decode layout [pos][k | v]
@@ -466,7 +476,7 @@ static int run_encoder(wm_handle* h) {
     memset(&a, 0, sizeof a);
     a.A = h->enc16; a.lda = d; a.W = wptr<__half>(h, p + "ckv_w"); a.bias = wptr<float>(h, p + "ckv_b");
     a.M = S; a.N = 2 * d; a.K = d; a.epi = ENC_EPI_BIAS_F16; a.out16 = h->cross_kv[i]; a.ldo16 = 2 * d;
-    CK(enc_gemm(a, s, nl));
+    CK(gemm_dispatch(h, a, s, nl));
   }
   return WM_OK;
 }
@@ -483,12 +493,12 @@ static int finish_encode(wm_handle* h) {
 }
 
 extern "C" int wm_encode_pcm(wm_handle* h, const float* pcm, int32_t n) {
-  if (!h || !pcm || n < 0) return WM_ERR_INVALID;
+  if (!h || n < 0 || (!pcm && n > 0)) return WM_ERR_INVALID;   // an empty clip (n == 0) is valid: 30 s of silence
   if (!h->wready) return fail(h, WM_ERR_STATE, "weights not loaded");
   CK(cudaSetDevice(h->device));
   h->launches[0] = h->launches[1] = 0;
   const int m = n < kSamples ? n : kSamples;
-  memcpy(h->h_stage, pcm, (size_t)m * sizeof(float));
+  if (m > 0) memcpy(h->h_stage, pcm, (size_t)m * sizeof(float));
   if (m < kSamples) memset(h->h_stage + m, 0, (size_t)(kSamples - m) * sizeof(float));
   CK(cudaEventRecord(h->ev[0], h->stream));
   CK(cudaMemcpyAsync(h->pcm, h->h_stage, (size_t)kSamples * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -677,6 +687,55 @@ extern "C" int64_t wm_last_launches(wm_handle* h, int32_t what) {
   if (what == 1) return h->launches[0] + h->launches[1];
   if (what == 2) return h->launches[2];
   return -1;
+}
+extern "C" int wm_set_option(wm_handle* h, const char* key, int32_t value) {
+  if (!h || !key) return WM_ERR_INVALID;
+  const std::string k(key);
+  if (k == "decode_mode") {
+    if (value < 0 || value > 2) return fail(h, WM_ERR_INVALID, "decode_mode must be 0, 1 or 2");
+    h->decode_mode = value;
+    return WM_OK;
+  }
+  if (k == "profile") {
+    // stage timeline of the persistent ring kernel (debug): buffer [2][n_instr][3] u64
+    CK(cudaSetDevice(h->device));
+    if (value && !h->prof) CK(dalloc(&h->prof, (size_t)2 * h->hm.prog_off[3] * 3));
+    h->hm.prof = value ? h->prof : nullptr;
+    CK(cudaMemcpy(h->dm, &h->hm, sizeof(DecModel), cudaMemcpyHostToDevice));
+    return WM_OK;
+  }
+  if (k == "enc_gemm") {
+    if (value == 1 && !h->tc_ok) return fail(h, WM_ERR_UNSUPPORTED, "tcgen05 GEMM unavailable (cuTensorMapEncodeTiled not found)");
+    if (value < 0 || value > 1) return fail(h, WM_ERR_INVALID, "enc_gemm must be 0 (mma.sync) or 1 (tcgen05)");
+    h->enc_gemm_impl = value;
+    return WM_OK;
+  }
+  return fail(h, WM_ERR_INVALID, "unknown option " + k);
+}
+// Stage timeline of the last persistent-ring iteration (option "profile" = 1): rows of
+// {stage, mode, layer, body_ns(cta 0), barrier_ns(cta 0), body_ns(last cta), barrier_ns(last cta)}
+extern "C" int wm_get_stage_profile(wm_handle* h, int64_t* out, int32_t cap_rows, int32_t* n_rows) {
+  if (!h || !out || !n_rows) return WM_ERR_INVALID;
+  if (!h->prof) return fail(h, WM_ERR_STATE, "profiling is off (wm_set_option(h, \"profile\", 1))");
+  CK(cudaSetDevice(h->device));
+  const int n = h->hm.prog_off[3];
+  std::vector<unsigned long long> raw((size_t)2 * n * 3);
+  std::vector<int> prog((size_t)n * 3);
+  CK(cudaMemcpy(raw.data(), h->prof, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(prog.data(), h->prog, prog.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  int rows = 0;
+  for (int i = 0; i < n && rows < cap_rows; ++i) {
+    const unsigned long long* a = &raw[(size_t)i * 3];
+    const unsigned long long* b = &raw[((size_t)n + i) * 3];
+    if (a[0] == 0) continue;   // stage not executed in the last iteration (sweep A skipped)
+    int64_t* o = out + (size_t)rows * 7;
+    o[0] = prog[i * 3]; o[1] = prog[i * 3 + 1]; o[2] = prog[i * 3 + 2];
+    o[3] = (int64_t)(a[1] - a[0]); o[4] = (int64_t)(a[2] - a[1]);
+    o[5] = (int64_t)(b[1] - b[0]); o[6] = (int64_t)(b[2] - b[1]);
+    ++rows;
+  }
+  *n_rows = rows;
+  return WM_OK;
 }
 extern "C" int wm_set_decode_mode(wm_handle* h, int32_t mode) {
   if (!h) return WM_ERR_INVALID;

@@ -53,6 +53,10 @@ cudaError_t enc_gemm_configure();
 cudaError_t enc_layernorm(const float* x, const float* g, const float* b, __half* y16, float* y32, int M, int d,
                           cudaStream_t s, int64_t* n_launch);
 
+// ---- enc_gemm_tc.cu (tcgen05 + TMA + TMEM) ----
+cudaError_t enc_gemm_tc(const EncGemmArgs& a, int a_rows, cudaStream_t s, int64_t* n_launch);
+cudaError_t enc_gemm_tc_configure();
+
 // ---- enc_attn.cu ----
 // qkv: fp16 [S_pad, 3d] (q pre-scaled | k | v); out: fp16 [S_pad, d]; full (non-causal) attention over S keys
 cudaError_t enc_attention(const __half* qkv, __half* out, int S, int d, int H, cudaStream_t s, int64_t* n_launch);

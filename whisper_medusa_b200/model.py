@@ -160,12 +160,11 @@ class WhisperMedusaModel:
         else:
             import torch.distributed as dist
 
+            from .parallel import broadcast_packed_weights
+
             with torch.cuda.device(index):
-                dev_blob = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
-                if dist.get_rank() == broadcast_src:
-                    blob = pack_blob(handle, self.config, self._state_dict)
-                    dev_blob.copy_(blob)
-                dist.broadcast(dev_blob, src=broadcast_src)
+                blob = pack_blob(handle, self.config, self._state_dict) if dist.get_rank() == broadcast_src else None
+                dev_blob = broadcast_packed_weights(nbytes, broadcast_src, blob, self._device)
                 torch.cuda.synchronize(index)
             self._wblob_dev = dev_blob  # keep alive: the engine does not own it
             _check(lib, handle, lib.wm_adopt_weights(handle, C.c_void_p(dev_blob.data_ptr()), nbytes), "wm_adopt_weights")
@@ -200,6 +199,12 @@ class WhisperMedusaModel:
         ``"persistent_simple"``: the same without the ring (grid barriers only)."""
         self._require_engine()
         _lib.load().wm_set_decode_mode(self._handle, {"graph": 0, "persistent_simple": 1, "persistent": 2}[mode])
+
+    def set_option(self, key: str, value: int) -> None:
+        """Engine options (``wm_set_option``): ``enc_gemm`` 0 = mma.sync, 1 = tcgen05/TMA/TMEM encoder GEMM."""
+        self._require_engine()
+        lib = _lib.load()
+        _check(lib, self._handle, lib.wm_set_option(self._handle, key.encode(), int(value)), f"wm_set_option({key})")
 
     def _require_engine(self):
         if self._handle is None:
