@@ -9,11 +9,22 @@
 #define WM_MAX_DEC_LAYERS 40
 #define WM_MAX_POS 512       // self-KV rows allocated per layer (448 + tree slack)
 #define WM_CROSS_CHUNKS 8    // cross-attention key chunks per head (flash-decoding split)
-#define WM_DEC_THREADS 512   // threads per CTA of the decode GEMM stages (16 warps)
+#define WM_DEC_THREADS 480   // compute threads per decode CTA (15 warps; the ring kernel adds a producer warp -> 512)
 
 namespace wm {
 
 struct StageInstr;
+// one ring chunk: `nrows` (<= 16) weight rows of d fp16 columns, row r at src + r * row_bytes
+struct ChunkDesc {
+  const void* src;
+  uint32_t row_bytes;
+  uint32_t nrows;
+};
+
+// Barrier over the WM_DEC_THREADS compute threads of a decode CTA.  The persistent ring kernel has
+// one extra warp (the weight producer) that never joins it, hence a named barrier instead of
+// __syncthreads(); in the 512-thread kernels it is simply "all threads".
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n"(WM_DEC_THREADS) : "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -152,6 +163,10 @@ struct DecModel {
   // stage program of the persistent ring kernel: {stage, mode, layer} triples; lists [off[i], off[i+1])
   const struct StageInstr* prog;
   int prog_off[4];
+  // per-CTA weight-chunk schedule of the ring producer (built by the host once the weights are bound):
+  // chunk_tab[chunk_off[cta*4 + list] .. chunk_off[cta*4 + list + 1]) in consumption order
+  const struct ChunkDesc* chunk_tab;
+  const int* chunk_off;
   DecState* st;
   unsigned int* bar;  // grid-barrier words for the persistent kernel
   unsigned long long* prof;  // optional stage timeline [2 CTAs][n_instr][3] (ns), null = off

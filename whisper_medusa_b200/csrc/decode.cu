@@ -11,6 +11,7 @@
 // skinny GEMMs (T <= 16 rows) run on mma.sync m16n8k16 with the fp32 activation split into
 // fp16 hi + lo parts (two MMAs), which keeps ~22 mantissa bits of the activation; the path is
 // HBM-bound (weights are streamed exactly once per pass), not tensor-bound.
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -59,7 +60,7 @@ __device__ void stage_embed(const DecModel* m, int mode, int cta, int ncta) {
     const __half* e = m->embed + (size_t)tok * d;
     const float* p = m->pos + (size_t)(g.base + t) * d;
     float* x = m->x + (size_t)t * d;
-    for (int j = threadIdx.x; j < d; j += blockDim.x) x[j] = __half2float(e[j]) + p[j];
+    for (int j = threadIdx.x; j < d; j += WM_DEC_THREADS) x[j] = __half2float(e[j]) + p[j];
   }
 }
 
@@ -150,7 +151,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmDesc& g, int token, int 
 
 __device__ void stage_gemm(const GemmDesc& g, int cta, int ncta, unsigned char* smem_raw) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nwarps = blockDim.x >> 5;
+  const int nwarps = (WM_DEC_THREADS >> 5);
   const int gq = lane >> 2, tq = lane & 3;
   const int K = g.K, N = g.N;
   const int nph = gemm_nphase(K);
@@ -180,7 +181,7 @@ __device__ void stage_gemm(const GemmDesc& g, int cta, int ncta, unsigned char* 
 
   for (int ph = 0; ph < nph; ++ph) {
     // ---- stage the activation slice as fp16 hi/lo ----
-    if (ph > 0) __syncthreads();
+    if (ph > 0) cta_sync();
     if (g.xsrc == XS_LN) {
       // LayerNorm over the full row (nph == 1 for LN stages: K = d <= 2048)
       for (int r = warp; r < 16; r += nwarps) {
@@ -205,7 +206,7 @@ __device__ void stage_gemm(const GemmDesc& g, int cta, int ncta, unsigned char* 
         }
       }
     } else {
-      for (int idx = tid; idx < 16 * KPH; idx += blockDim.x) {
+      for (int idx = tid; idx < 16 * KPH; idx += WM_DEC_THREADS) {
         int r = idx / KPH, j = idx - r * KPH;
         float y = (r < T) ? g.X[(size_t)(g.x_row0 + r) * K + ph * KPH + j] : 0.f;
         __half h = __float2half_rn(y);
@@ -213,7 +214,7 @@ __device__ void stage_gemm(const GemmDesc& g, int cta, int ncta, unsigned char* 
         xlo[r * xstride + j] = __float2half_rn(y - __half2float(h));
       }
     }
-    __syncthreads();
+    cta_sync();
 
     // ---- stream the weights ----
 #pragma unroll
@@ -292,8 +293,8 @@ __device__ void stage_gemm(const GemmDesc& g, int cta, int ncta, unsigned char* 
         for (int e = 0; e < 8; ++e) partial[(size_t)item * 256 + e * 32 + lane] = acc[r][e];
       }
     }
-    __syncthreads();
-    for (int o = tid; o < units * 256; o += blockDim.x) {
+    cta_sync();
+    for (int o = tid; o < units * 256; o += WM_DEC_THREADS) {
       const int u = o >> 8, el = o & 255;
       const int e = el >> 5, ln = el & 31;
       const int j = e >> 2, i = e & 3;
@@ -320,16 +321,16 @@ __device__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta,
   float* s_p = s_q + 64;                                      // [WM_MAX_POS]
   float* s_red = s_p + WM_MAX_POS;                            // [64]
   float* s_acc = s_red + 64;                                  // [64 groups][64]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (WM_DEC_THREADS >> 5);
   for (int item = cta; item < H * g.T; item += ncta) {
     const int h = item / g.T, t = item - h * g.T;
     const int nk = g.base + t + 1;
-    __syncthreads();
+    cta_sync();
     if (tid < 64) s_q[tid] = m->q[(size_t)t * d + h * 64 + tid];
-    __syncthreads();
+    cta_sync();
     // scores
     float lmax = -INFINITY;
-    for (int j = tid; j < nk; j += blockDim.x) {
+    for (int j = tid; j < nk; j += WM_DEC_THREADS) {
       const uint4* kp = reinterpret_cast<const uint4*>(L.self_k + (size_t)j * d + h * 64);
       float s = 0.f;
 #pragma unroll
@@ -349,23 +350,23 @@ __device__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta,
     }
     lmax = warp_max(lmax);
     if (lane == 0) s_red[warp] = lmax;
-    __syncthreads();
+    cta_sync();
     float gmax = -INFINITY;
     for (int w = 0; w < nwarps; ++w) gmax = fmaxf(gmax, s_red[w]);
-    __syncthreads();
+    cta_sync();
     float lsum = 0.f;
-    for (int j = tid; j < nk; j += blockDim.x) {
+    for (int j = tid; j < nk; j += WM_DEC_THREADS) {
       float p = expf(s_p[j] - gmax);
       s_p[j] = p;
       lsum += p;
     }
     lsum = warp_sum(lsum);
     if (lane == 0) s_red[32 + warp] = lsum;
-    __syncthreads();
+    cta_sync();
     float gsum = 0.f;
     for (int w = 0; w < nwarps; ++w) gsum += s_red[32 + w];
     // P * V : thread = (key group kg, dim group dg of 8 dims)
-    const int dg = tid & 7, kg = tid >> 3, ngroups = blockDim.x >> 3;
+    const int dg = tid & 7, kg = tid >> 3, ngroups = (WM_DEC_THREADS >> 3);
     float a[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) a[e] = 0.f;
@@ -382,7 +383,7 @@ __device__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta,
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) s_acc[kg * 64 + dg * 8 + e] = a[e];
-    __syncthreads();
+    cta_sync();
     if (tid < 64) {
       float o = 0.f;
       for (int gI = 0; gI < ngroups; ++gI) o += s_acc[gI * 64 + tid];
@@ -414,26 +415,26 @@ __device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta
   float* sS = reinterpret_cast<float*>(sV + WM_CH_MAX * 64);        // [16][WM_CH_MAX]
   float* sQ = sS + WM_MAX_T * WM_CH_MAX;                            // [16][64]
   float* sM = sQ + WM_MAX_T * 64;                                   // [16] max, [16] sum
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (WM_DEC_THREADS >> 5);
   const int T = g.T;
   __shared__ int s_last;
   for (int item = cta; item < H * WM_CROSS_CHUNKS; item += ncta) {
     const int h = item / WM_CROSS_CHUNKS, c = item - h * WM_CROSS_CHUNKS;
     const int j0 = c * CH, nk = max(0, min(S, j0 + CH) - j0);
-    __syncthreads();
-    for (int idx = tid; idx < nk * 8; idx += blockDim.x) {
+    cta_sync();
+    for (int idx = tid; idx < nk * 8; idx += WM_DEC_THREADS) {
       int j = idx >> 3, part = idx & 7;
       const __half* src = L.cross_kv + (size_t)(j0 + j) * 2 * d + h * 64 + part * 8;
       *reinterpret_cast<uint4*>(sK + j * 72 + part * 8) = ldg_nc_v4(src);
       *reinterpret_cast<uint4*>(sV + j * 64 + part * 8) = ldg_nc_v4(src + d);
     }
-    for (int idx = tid; idx < T * 64; idx += blockDim.x) {
+    for (int idx = tid; idx < T * 64; idx += WM_DEC_THREADS) {
       int t = idx >> 6, e = idx & 63;
       sQ[idx] = m->q[(size_t)t * d + h * 64 + e];
     }
-    __syncthreads();
+    cta_sync();
     // scores for all (t, j)
-    for (int idx = tid; idx < T * nk; idx += blockDim.x) {
+    for (int idx = tid; idx < T * nk; idx += WM_DEC_THREADS) {
       int t = idx / nk, j = idx - t * nk;
       const float* q = sQ + t * 64;
       const uint4* kp = reinterpret_cast<const uint4*>(sK + j * 72);
@@ -451,7 +452,7 @@ __device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta
       }
       sS[t * WM_CH_MAX + j] = s * 0.125f;  // head_dim^-0.5
     }
-    __syncthreads();
+    cta_sync();
     // per-row max / exp / sum : warp per row
     for (int t = warp; t < T; t += nwarps) {
       float mx = -INFINITY;
@@ -466,7 +467,7 @@ __device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta
       sum = warp_sum(sum);
       if (lane == 0) { sM[t] = mx; sM[WM_MAX_T + t] = sum; }
     }
-    __syncthreads();
+    cta_sync();
     // P * V : warp per row t; lane = (kg of 4, dg of 8)
     for (int t = warp; t < T; t += nwarps) {
       const int dg = lane & 7, kg = lane >> 3;
@@ -499,17 +500,17 @@ __device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta
     // The chunk that arrives last for this head folds the WM_CROSS_CHUNKS partials (always in chunk
     // order => deterministic) -- no separate combine stage / grid barrier.
     __threadfence();
-    __syncthreads();
+    cta_sync();
     if (tid == 0) {
       const unsigned int prev = atomicAdd(&m->cross_cnt[h], 1u);
       s_last = (prev == WM_CROSS_CHUNKS - 1) ? 1 : 0;
       if (s_last) m->cross_cnt[h] = 0u;   // everybody has arrived: re-arm for the next layer
     }
-    __syncthreads();
+    cta_sync();
     if (s_last) {
       __threadfence();
       const size_t cstride = (size_t)WM_MAX_T * (WM_HEAD_DIM + 2);
-      for (int idx = tid; idx < T * 64; idx += blockDim.x) {
+      for (int idx = tid; idx < T * 64; idx += WM_DEC_THREADS) {
         const int t = idx >> 6, e = idx & 63;
         const float* base = m->cross_part + ((size_t)h * WM_CROSS_CHUNKS * WM_MAX_T + t) * (WM_HEAD_DIM + 2);
         float M = -INFINITY;
@@ -537,7 +538,7 @@ __device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta
 __device__ void stage_final_ln(const DecModel* m, int mode, int cta, int ncta) {
   PassGeom g = pass_geom(m, mode);
   const int d = m->d;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (WM_DEC_THREADS >> 5);
   for (int t = cta * nwarps + warp; t < g.T; t += ncta * nwarps) {
     const float* x = m->x + (size_t)t * d;
     float s = 0.f;
@@ -559,11 +560,11 @@ __device__ void stage_final_ln(const DecModel* m, int mode, int cta, int ncta) {
 __device__ void stage_copy_hidden_to_x(const DecModel* m, int mode, int cta, int ncta) {
   PassGeom g = pass_geom(m, mode);
   const int total = g.T * m->d;
-  for (int idx = cta * blockDim.x + threadIdx.x; idx < total; idx += ncta * blockDim.x) m->x[idx] = m->hidden[idx];
+  for (int idx = cta * WM_DEC_THREADS + threadIdx.x; idx < total; idx += ncta * WM_DEC_THREADS) m->x[idx] = m->hidden[idx];
 }
 // block type, tail: the block runs on the carried hidden state (one row); vocab row 0 = base logits
 __device__ void stage_tail_seed(const DecModel* m, int cta, int ncta) {
-  for (int idx = cta * blockDim.x + threadIdx.x; idx < m->d; idx += ncta * blockDim.x) {
+  for (int idx = cta * WM_DEC_THREADS + threadIdx.x; idx < m->d; idx += ncta * WM_DEC_THREADS) {
     const float y = m->carry[idx];
     m->x[idx] = y;
     m->head_h[idx] = y;
@@ -586,16 +587,16 @@ __device__ __forceinline__ float processed_logit(const float* row, int j, const 
 }
 
 __device__ void block_argmax(float& v, int& i, float* s_val, int* s_idx) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (WM_DEC_THREADS >> 5);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     float ov = __shfl_xor_sync(0xffffffffu, v, o);
     int oi = __shfl_xor_sync(0xffffffffu, i, o);
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
   }
-  __syncthreads();
+  cta_sync();
   if (lane == 0) { s_val[warp] = v; s_idx[warp] = i; }
-  __syncthreads();
+  cta_sync();
   v = s_val[0]; i = s_idx[0];
   for (int w = 1; w < nwarps; ++w) {
     float ov = s_val[w]; int oi = s_idx[w];
@@ -603,11 +604,11 @@ __device__ void block_argmax(float& v, int& i, float* s_val, int* s_idx) {
   }
 }
 __device__ float block_sum(float v, float* s_val) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (WM_DEC_THREADS >> 5);
   v = warp_sum(v);
-  __syncthreads();
+  cta_sync();
   if (lane == 0) s_val[warp] = v;
-  __syncthreads();
+  cta_sync();
   float s = 0.f;
   for (int w = 0; w < nwarps; ++w) s += s_val[w];
   return s;
@@ -627,7 +628,7 @@ __device__ void stage_select(const DecModel* m, int mode, int cta, int ncta, uns
     const float* row = logits + (size_t)r * V;
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    for (int j = threadIdx.x; j < V; j += WM_DEC_THREADS) {
       float v = processed_logit(row, j, m->tok_mask, begin_on, eos, pen);
       if (v > bv) { bv = v; bi = j; }   // ascending j per thread => first maximum kept
     }
@@ -644,11 +645,11 @@ __device__ void stage_select(const DecModel* m, int mode, int cta, int ncta, uns
     const float inv_t = 1.0f / temp;
     const float mx = bv * inv_t;   // max of the temperature-scaled row (temp > 0)
     float z = 0.f;
-    for (int j = threadIdx.x; j < V; j += blockDim.x)
+    for (int j = threadIdx.x; j < V; j += WM_DEC_THREADS)
       z += expf(processed_logit(row, j, m->tok_mask, begin_on, eos, pen) * inv_t - mx);
     z = block_sum(z, s_val);
     float ent = 0.f;
-    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    for (int j = threadIdx.x; j < V; j += WM_DEC_THREADS) {
       float p = expf(processed_logit(row, j, m->tok_mask, begin_on, eos, pen) * inv_t - mx) / z;
       ent += p * logf(p + 1e-5f);
     }
@@ -705,11 +706,11 @@ __device__ void stage_accept(const DecModel* m) {
     if (done) st->done = 1;
     s_a = a;
   }
-  __syncthreads();
+  cta_sync();
   const int a = s_a;
   if (a >= 1) {
     const float* src = m->hidden + (size_t)a * m->d;
-    for (int j = threadIdx.x; j < m->d; j += blockDim.x) m->carry[j] = src[j];
+    for (int j = threadIdx.x; j < m->d; j += WM_DEC_THREADS) m->carry[j] = src[j];
   }
 }
 
@@ -862,7 +863,7 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 // counter (reset by the host before every wm_generate): barrier number e completes when it
 // reaches ncta * e.
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch, int ncta) {
-  __syncthreads();
+  cta_sync();
   if (threadIdx.x == 0) {
     epoch += 1;
     const unsigned int target = (unsigned int)ncta * epoch;
@@ -871,7 +872,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ep
     while (ld_acquire_u32(&bar[0]) < target) { }
     __threadfence();
   }
-  __syncthreads();
+  cta_sync();
 }
 
 __global__ void __launch_bounds__(WM_DEC_THREADS, 1)
@@ -916,9 +917,43 @@ void dec_build_program(int n_layers, int has_block, std::vector<int>& flat, int 
 
 size_t dec_ring_smem_bytes(int d) { return ring_smem_bytes(d); }
 
+// Per-CTA chunk schedule of the ring producer, in exactly the order stage_gemm_ring consumes:
+// for every GEMM stage of the program with rows for the CTA: for seg (K / d): for unit (16 rows).
+// `hm` is the HOST copy of the model (device pointers inside).  off has 4 entries per CTA.
+void dec_build_chunk_table(const DecModel& hm, int ncta, std::vector<ChunkDesc>& tab, std::vector<int>& off) {
+  std::vector<int> flat;
+  int poff[4];
+  dec_build_program(hm.n_layers, hm.has_block, flat, poff);
+  tab.clear();
+  off.assign((size_t)ncta * 4, 0);
+  for (int cta = 0; cta < ncta; ++cta) {
+    for (int list = 0; list < 3; ++list) {
+      off[(size_t)cta * 4 + list] = (int)tab.size();
+      for (int ip = poff[list]; ip < poff[list + 1]; ++ip) {
+        const int stage = flat[ip * 3], mode = flat[ip * 3 + 1], layer = flat[ip * 3 + 2];
+        if (!is_gemm_stage(stage)) continue;
+        const WDesc w = stage_weights(&hm, stage, mode, layer);
+        int nb, nr;
+        cta_rows(w.N, cta, ncta, nb, nr);
+        if (nr == 0) continue;
+        const int units = (nr + 15) >> 4, segs = w.K / hm.d;
+        for (int sg = 0; sg < segs; ++sg)
+          for (int u = 0; u < units; ++u) {
+            ChunkDesc c;
+            c.src = w.W + (size_t)(nb + u * 16) * w.K + (size_t)sg * hm.d;
+            c.row_bytes = (uint32_t)(w.K * sizeof(__half));
+            c.nrows = (uint32_t)std::min(16, nr - u * 16);
+            tab.push_back(c);
+          }
+      }
+    }
+    off[(size_t)cta * 4 + 3] = (int)tab.size();
+  }
+}
+
 cudaError_t dec_launch_iteration_ring(const DecModel* dm, const DecHostInfo& hi, cudaStream_t s) {
   void* args[] = {(void*)&dm};
-  return cudaLaunchCooperativeKernel((void*)dec_iteration_ring_kernel, dim3(hi.n_sm), dim3(WM_DEC_THREADS), args,
+  return cudaLaunchCooperativeKernel((void*)dec_iteration_ring_kernel, dim3(hi.n_sm), dim3(WM_RING_THREADS), args,
                                      hi.smem_ring, s);
 }
 

@@ -6,17 +6,22 @@
 // needs is static: for every GEMM stage it owns a fixed, contiguous range of rows of W.  So each
 // CTA streams its rows for the upcoming stages through a shared-memory ring with bulk async
 // copies (cp.async.bulk -> mbarrier complete_tx; SASS UBLKCP), independently of the activation
-// dependency chain: the copies for stages s+1, s+2, ... are in flight while the CTA sits in the
-// grid barrier of stage s.  When a stage's activations finally arrive, its weights are already
-// on-chip and the stage costs: X staging (L2) + a few MMAs out of shared memory + epilogue.
+// dependency chain: the copies for stages s+1, s+2, ... are in flight while the compute warps sit
+// in the grid barrier of stage s.  When a stage's activations finally arrive, its weights are
+// already on-chip and the stage costs: X staging (L2) + a few MMAs out of shared memory + epilogue.
 //
-// Ring geometry: a "chunk" = up to 16 weight rows x d columns (fp16), one row per bulk copy, row
-// stride d*2 + 64 B (bank-conflict-free LDS.128 of the B fragments).  WM_RING_G chunks are
-// resident.  Chunks are consumed in program order; the producer (thread 0) re-fills a slot as
-// soon as the chunk that lived there has been consumed.
+// Roles: warps 0..15 = compute (WM_DEC_THREADS threads, named barrier 1), warp 16 = producer.
+// The producer walks a per-CTA chunk table that the host builds once per model (no pointer
+// chasing on the device), waits on `empty[slot]`, arms `full[slot]` with the byte count and lets
+// lanes 0..nrows-1 issue one bulk copy per weight row.
+//
+// Ring geometry: a "chunk" = up to 16 weight rows x d columns (fp16), row stride d*2 + 64 B
+// (bank-conflict-free LDS.128 of the B fragments); WM_RING_G chunks are resident; chunks are
+// consumed in program order.
 #pragma once
 
 #define WM_RING_G 3
+#define WM_RING_THREADS (WM_DEC_THREADS + 32)
 
 struct StageInstr { int stage, mode, layer; };
 
@@ -26,6 +31,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -45,21 +53,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
-__device__ __forceinline__ bool is_gemm_stage(int st) {
+__host__ __device__ __forceinline__ bool is_gemm_stage(int st) {
   return st == ST_QKV || st == ST_OPROJ || st == ST_CROSS_Q || st == ST_CROSS_O || st == ST_FC1 || st == ST_FC2 ||
          st == ST_HEADS || st == ST_VOCAB;
 }
 
 // static part of a GEMM stage (what the producer needs): weights and shape
 struct WDesc { const __half* W; int N, K; };
-__device__ __forceinline__ WDesc stage_weights(const DecModel* m, int stage, int mode, int layer) {
+__host__ __device__ inline WDesc stage_weights(const DecModel* m, int stage, int mode, int layer) {
   const DecLayer& L = m->layers[layer];
   const int d = m->d;
   WDesc w;
@@ -79,83 +86,45 @@ __device__ __forceinline__ WDesc stage_weights(const DecModel* m, int stage, int
   return w;
 }
 
-__device__ __forceinline__ void cta_rows(int N, int cta, int ncta, int& n_begin, int& n_rows) {
+__host__ __device__ __forceinline__ void cta_rows(int N, int cta, int ncta, int& n_begin, int& n_rows) {
   const int rows_per = N / ncta, rem = N % ncta;
-  n_begin = cta * rows_per + min(cta, rem);
+  n_begin = cta * rows_per + (cta < rem ? cta : rem);
   n_rows = rows_per + (cta < rem ? 1 : 0);
 }
 
-// Producer-side iterator over the chunks of one iteration, in consumption order.
-struct ChunkIter {
-  const StageInstr* prog;
-  int ip, ip_end;         // current instruction / end of the current list
-  int list;               // 0 = sweep A, 1 = tail, 2 = verify
-  const __half* W;        // current GEMM stage
-  int K, n_begin, n_rows, units, segs;
-  int sg, u;
-  bool valid;
-};
-
 struct RingCtx {
-  const DecModel* m;
   unsigned char* ring;     // WM_RING_G slots
-  uint64_t* full;          // WM_RING_G mbarriers
+  uint64_t* full;          // WM_RING_G mbarriers (producer -> compute)
+  uint64_t* empty;         // WM_RING_G mbarriers (compute -> producer)
   int row_stride;          // bytes
   int slot_bytes;
+  int d;
   int cta, ncta;
-  unsigned int issued;     // chunks issued (thread 0 only)
-  unsigned int consumed;   // chunks consumed (uniform)
-  ChunkIter it;            // thread 0 only
+  unsigned int consumed;   // chunks consumed so far in this launch (uniform across the compute warps)
 };
 
-__device__ void chunk_iter_seek(RingCtx& rc) {
-  // position `it` on the first chunk of the next GEMM stage with rows for this CTA
-  ChunkIter& it = rc.it;
-  const DecModel* m = rc.m;
-  while (true) {
-    while (it.ip >= it.ip_end) {
-      it.list += 1;
-      if (it.list > 2) { it.valid = false; return; }
-      it.ip = m->prog_off[it.list];
-      it.ip_end = m->prog_off[it.list + 1];
+// ---------------------------------------------------------------------------------------------
+// producer warp: stream the chunk table through the ring
+// ---------------------------------------------------------------------------------------------
+__device__ void ring_producer(const RingCtx& rc, const ChunkDesc* __restrict__ tab, int first, int last) {
+  const int lane = threadIdx.x & 31;
+  for (int c = first; c < last; ++c) {
+    const unsigned int k = (unsigned int)(c - first);
+    const int slot = k % WM_RING_G;
+    const unsigned int round = k / WM_RING_G;
+    const ChunkDesc dsc = tab[c];                       // same address on every lane: one broadcast load
+    if (lane == 0) {
+      while (!mbar_try_wait(rc.empty + slot, (round & 1) ^ 1)) { }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the slot vs async writes
+      mbar_expect_tx(rc.full + slot, (uint32_t)(dsc.nrows * rc.d * 2));
     }
-    const StageInstr in = it.prog[it.ip];
-    if (is_gemm_stage(in.stage)) {
-      WDesc w = stage_weights(m, in.stage, in.mode, in.layer);
-      int nb, nr;
-      cta_rows(w.N, rc.cta, rc.ncta, nb, nr);
-      if (nr > 0) {
-        it.W = w.W; it.K = w.K; it.n_begin = nb; it.n_rows = nr;
-        it.units = (nr + 15) >> 4; it.segs = w.K / m->d; it.sg = 0; it.u = 0; it.valid = true;
-        return;
-      }
+    __syncwarp();
+    if (lane < dsc.nrows) {
+      bulk_g2s(rc.ring + (size_t)slot * rc.slot_bytes + (size_t)lane * rc.row_stride,
+               reinterpret_cast<const unsigned char*>(dsc.src) + (size_t)lane * dsc.row_bytes, (uint32_t)(rc.d * 2),
+               rc.full + slot);
     }
-    it.ip += 1;
-  }
-}
-__device__ __forceinline__ void chunk_iter_next(RingCtx& rc) {
-  ChunkIter& it = rc.it;
-  it.u += 1;
-  if (it.u >= it.units) { it.u = 0; it.sg += 1; }
-  if (it.sg >= it.segs) { it.ip += 1; chunk_iter_seek(rc); }
-}
-
-// thread 0: issue bulk copies for as many future chunks as there are free slots
-__device__ void ring_prefetch(RingCtx& rc) {
-  const int d = rc.m->d;
-  while (rc.it.valid && rc.issued - rc.consumed < WM_RING_G) {
-    const ChunkIter& it = rc.it;
-    const int slot = rc.issued % WM_RING_G;
-    const int r0 = it.u * 16;
-    const int nr = min(16, it.n_rows - r0);
-    uint64_t* bar = rc.full + slot;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the slot vs async writes
-    mbar_expect_tx(bar, (uint32_t)(nr * d * 2));
-    const __half* src = it.W + (size_t)(it.n_begin + r0) * it.K + (size_t)it.sg * d;
-    unsigned char* dst = rc.ring + (size_t)slot * rc.slot_bytes;
-    for (int r = 0; r < nr; ++r) bulk_g2s(dst + (size_t)r * rc.row_stride, src + (size_t)r * it.K, (uint32_t)(d * 2), bar);
-    rc.issued += 1;
-    chunk_iter_next(rc);
+    __syncwarp();
   }
 }
 
@@ -177,14 +146,14 @@ __device__ __forceinline__ void store_hilo4(__half* hi, __half* lo, float4 y) {
 #define WM_LN_MAXV 10   // float4 per lane: d <= 1280 (every Whisper size)
 
 __device__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __half* xlo, int xstride, int& rows_dirty) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = WM_DEC_THREADS >> 5;
   const int T = g.x_rows;
   // rows that still hold data of an earlier, taller stage must read as zero
   if (rows_dirty > T) {
     const int n16 = (rows_dirty - T) * xstride / 8;   // uint4 = 8 halfs; xstride % 8 == 0
     uint4* zh = reinterpret_cast<uint4*>(xhi + (size_t)T * xstride);
     uint4* zl = reinterpret_cast<uint4*>(xlo + (size_t)T * xstride);
-    for (int i = tid; i < n16; i += blockDim.x) { zh[i] = make_uint4(0, 0, 0, 0); zl[i] = make_uint4(0, 0, 0, 0); }
+    for (int i = tid; i < n16; i += WM_DEC_THREADS) { zh[i] = make_uint4(0, 0, 0, 0); zl[i] = make_uint4(0, 0, 0, 0); }
   }
   rows_dirty = T;
   if (g.xsrc == XS_LN) {
@@ -226,11 +195,11 @@ __device__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __h
   } else {
     const int d4 = d >> 2;
     const int total = T * d4;
-    for (int base = 0; base < total; base += 8 * blockDim.x) {
+    for (int base = 0; base < total; base += 8 * WM_DEC_THREADS) {
       float4 v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int idx = base + i * blockDim.x + tid;
+        const int idx = base + i * WM_DEC_THREADS + tid;
         if (idx < total) {
           const int r = idx / d4, c4 = idx - r * d4;
           v[i] = *reinterpret_cast<const float4*>(g.X + (size_t)(g.x_row0 + r) * g.K + (size_t)seg * d + c4 * 4);
@@ -238,7 +207,7 @@ __device__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __h
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int idx = base + i * blockDim.x + tid;
+        const int idx = base + i * WM_DEC_THREADS + tid;
         if (idx < total) {
           const int r = idx / d4, c4 = idx - r * d4;
           store_hilo4(xhi + (size_t)r * xstride + c4 * 4, xlo + (size_t)r * xstride + c4 * 4, v[i]);
@@ -249,16 +218,16 @@ __device__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __h
 }
 
 // ---------------------------------------------------------------------------------------------
-// GEMM stage fed from the ring
+// GEMM stage fed from the ring (compute warps)
 // ---------------------------------------------------------------------------------------------
 __device__ void stage_gemm_ring(RingCtx& rc, const GemmDesc& g, __half* xhi, __half* xlo, float* partial, int& rows_dirty) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
-  const int d = rc.m->d;
+  const int d = rc.d;
   const int xstride = d + WM_XPAD;
   int n_begin, n_rows;
   cta_rows(g.N, rc.cta, rc.ncta, n_begin, n_rows);
-  if (n_rows == 0) return;   // the producer skips such stages as well
+  if (n_rows == 0) return;   // the chunk table has no entry for such stages either
   const int units = (n_rows + 15) >> 4;
   const int segs = g.K / d;
   int nks = 8;               // k-slices per chunk: one warp each, both n8 tiles of the chunk
@@ -269,9 +238,9 @@ __device__ void stage_gemm_ring(RingCtx& rc, const GemmDesc& g, __half* xhi, __h
   float racc = 0.f;                      // multi-segment accumulator of output element `tid` (units == 1 when segs > 1)
 
   for (int sg = 0; sg < segs; ++sg) {
-    if (sg > 0) __syncthreads();
+    if (sg > 0) cta_sync();
     ring_stage_x(g, sg, d, xhi, xlo, xstride, rows_dirty);
-    __syncthreads();
+    cta_sync();
     for (int u = 0; u < units; ++u) {
       const unsigned int c = rc.consumed;
       const int slot = c % WM_RING_G;
@@ -312,10 +281,9 @@ __device__ void stage_gemm_ring(RingCtx& rc, const GemmDesc& g, __half* xhi, __h
           partial[(size_t)warp * 256 + (4 + e) * 32 + lane] = c1[e];
         }
       }
-      __syncthreads();   // partials visible; every read of the slot and of X (for this chunk) is done
-      // the slot is free: let the producer refill it while the epilogue runs
+      cta_sync();   // partials visible; every read of the slot (and of X for this chunk) is done
       rc.consumed = c + 1;
-      if (tid == 0) ring_prefetch(rc);
+      if (tid == 0) mbar_arrive(rc.empty + slot);   // hand the slot back to the producer
       if (tid < 256) {
         const int e = tid >> 5, ln = tid & 31;
         const int j = e >> 2, i = e & 3;
@@ -328,62 +296,67 @@ __device__ void stage_gemm_ring(RingCtx& rc, const GemmDesc& g, __half* xhi, __h
           if (sg == segs - 1) gemm_epilogue(g, token, n_begin + u * 16 + rloc, s, xhi, xlo, xstride);
         }
       }
-      __syncthreads();   // partial buffer reusable
+      cta_sync();   // partial buffer reusable
     }
   }
 }
 
-__host__ __device__ inline size_t ring_smem_bytes(int d) {
-  const size_t ring = (size_t)WM_RING_G * 16 * (d * 2 + 64);
+__host__ __device__ inline size_t ring_scratch_bytes(int d) {
   size_t scratch = (size_t)2 * 16 * (d + WM_XPAD) * sizeof(__half);
   if (scratch < cross_attn_smem_bytes()) scratch = cross_attn_smem_bytes();
   if (scratch < self_attn_smem_bytes()) scratch = self_attn_smem_bytes();
-  return ring + scratch + (size_t)8 * 256 * sizeof(float) + 64;
+  return (scratch + 127) / 128 * 128;
+}
+__host__ __device__ inline size_t ring_smem_bytes(int d) {
+  return (size_t)WM_RING_G * 16 * (d * 2 + 64) + ring_scratch_bytes(d) + (size_t)8 * 256 * sizeof(float) + 128;
 }
 
-__global__ void __launch_bounds__(WM_DEC_THREADS, 1)
+__global__ void __launch_bounds__(WM_RING_THREADS, 1)
 dec_iteration_ring_kernel(const DecModel* __restrict__ m) {
   extern __shared__ __align__(128) unsigned char smem[];
   const DecState* st = m->st;
   if (st->done) return;
   const int need_a = st->need_a;
   const int d = m->d;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const int warp = threadIdx.x >> 5;
   RingCtx rc;
-  rc.m = m;
+  rc.d = d;
   rc.row_stride = d * 2 + 64;
   rc.slot_bytes = 16 * rc.row_stride;
   rc.ring = smem;
-  size_t scratch = (size_t)2 * 16 * (d + WM_XPAD) * sizeof(__half);
-  if (scratch < cross_attn_smem_bytes()) scratch = cross_attn_smem_bytes();
-  if (scratch < self_attn_smem_bytes()) scratch = self_attn_smem_bytes();
   unsigned char* scratch_p = smem + (size_t)WM_RING_G * rc.slot_bytes;
   __half* xhi = reinterpret_cast<__half*>(scratch_p);
   __half* xlo = xhi + 16 * (d + WM_XPAD);
-  float* partial = reinterpret_cast<float*>(scratch_p + scratch);
+  float* partial = reinterpret_cast<float*>(scratch_p + ring_scratch_bytes(d));
   rc.full = reinterpret_cast<uint64_t*>(partial + 8 * 256);
-  rc.cta = blockIdx.x; rc.ncta = gridDim.x;
-  rc.issued = 0; rc.consumed = 0;
-  rc.it.prog = m->prog;
-  rc.it.list = need_a ? 0 : 1;
-  rc.it.ip = m->prog_off[rc.it.list];
-  rc.it.ip_end = m->prog_off[rc.it.list + 1];
-  rc.it.valid = false;
+  rc.empty = rc.full + WM_RING_G;
+  rc.cta = cta; rc.ncta = ncta;
+  rc.consumed = 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WM_RING_G; ++i) mbar_init(rc.full + i, 1);
+    for (int i = 0; i < WM_RING_G; ++i) { mbar_init(rc.full + i, 1); mbar_init(rc.empty + i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // the activation slice rows must read as zero beyond the rows a stage writes
+  __syncthreads();   // the only full-CTA barrier: after it the producer warp goes its own way
+
+  if (warp == WM_DEC_THREADS / 32) {
+    // ===== producer warp =====
+    const int* off = m->chunk_off + cta * 4;
+    ring_producer(rc, m->chunk_tab, need_a ? off[0] : off[1], off[3]);
+    return;
+  }
+
+  // ===== compute warps =====
   {
+    // the activation slice rows must read as zero beyond the rows a stage writes
     uint4* z = reinterpret_cast<uint4*>(scratch_p);
     const int n16 = (int)((size_t)2 * 16 * (d + WM_XPAD) * sizeof(__half) / 16);
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < n16; i += WM_DEC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) { chunk_iter_seek(rc); ring_prefetch(rc); }
+  cta_sync();
   int rows_dirty = 0;
   unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(&m->bar[2]);
   unsigned int* bar = m->bar;
-  const int cta = blockIdx.x, ncta = gridDim.x;
 
   for (int list = need_a ? 0 : 1; list <= 2; ++list) {
     const int i0 = m->prog_off[list], i1 = m->prog_off[list + 1];

@@ -62,6 +62,8 @@ struct wm_handle {
   unsigned int* bar = nullptr;
   int* prog = nullptr;
   unsigned long long* prof = nullptr;
+  ChunkDesc* chunk_tab = nullptr;
+  int* chunk_off = nullptr;
   DecHostInfo hi;
   std::map<int, cudaGraphExec_t> graph_a;  // sweep A, keyed by T
   cudaGraphExec_t graph_tail = nullptr, graph_b = nullptr;
@@ -316,7 +318,7 @@ extern "C" int wm_destroy(wm_handle* h) {
   for (auto p : h->self_k) F(p);
   for (auto p : h->self_v) F(p);
   F(h->hm.x); F(h->hm.q); F(h->hm.attn); F(h->hm.ffn_h); F(h->hm.hidden); F(h->hm.head_h); F(h->hm.carry); F(h->hm.cross_part); F(h->hm.cross_cnt);
-  F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->prog); F(h->prof); F(h->dm);
+  F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->prog); F(h->prof); F(h->chunk_tab); F(h->chunk_off); F(h->dm);
   if (h->wowned) F(h->wdev);
   if (h->h_state) cudaFreeHost(h->h_state);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -379,6 +381,20 @@ static int bind_weights(wm_handle* h) {
   m.pos = wptr<float>(h, "dec.pos");
   m.lnf_g = wptr<float>(h, "dec.lnf_g"); m.lnf_b = wptr<float>(h, "dec.lnf_b");
   m.heads_w = wptr<__half>(h, "heads_w"); m.heads_b = wptr<float>(h, "heads_b");
+  {
+    // weight-chunk schedule of the ring producer (depends on the weight addresses)
+    std::vector<ChunkDesc> tab;
+    std::vector<int> off;
+    dec_build_chunk_table(m, h->n_sm, tab, off);
+    if (h->chunk_tab) { cudaFree(h->chunk_tab); h->chunk_tab = nullptr; }
+    if (h->chunk_off) { cudaFree(h->chunk_off); h->chunk_off = nullptr; }
+    CK(cudaMalloc((void**)&h->chunk_tab, tab.size() * sizeof(ChunkDesc)));
+    CK(cudaMalloc((void**)&h->chunk_off, off.size() * sizeof(int)));
+    CK(cudaMemcpy(h->chunk_tab, tab.data(), tab.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->chunk_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    m.chunk_tab = h->chunk_tab;
+    m.chunk_off = h->chunk_off;
+  }
   CK(cudaMemcpy(h->dm, &m, sizeof m, cudaMemcpyHostToDevice));
   h->wready = true;
   return WM_OK;
