@@ -21,7 +21,7 @@ from whisper_medusa_b200 import WhisperMedusaModel, _lib  # noqa: E402
 from whisper_medusa_b200.synthetic import preset_config, synthetic_audio, synthetic_state_dict  # noqa: E402
 
 STAGES = ["EMBED", "QKV", "SELF_ATTN", "OPROJ", "CROSS_Q", "CROSS_ATTN", "CROSS_O", "FC1", "FC2", "FINAL_LN",
-          "COPY_HIDDEN", "TAIL_SEED", "HEADS", "VOCAB", "SELECT", "ACCEPT"]
+          "COPY_HIDDEN", "TAIL_SEED", "HEADS", "VOCAB", "SELECT1", "SELECT2", "SELECT_FIN", "ACCEPT"]
 MODES = ["A", "B", "TAIL"]
 
 
@@ -45,24 +45,27 @@ def main():
     tr = model.last_trace
     lib = _lib.load()
     cap = 4096
-    buf = (C.c_int64 * (cap * 7))()
+    buf = (C.c_int64 * (cap * 11))()
     n = C.c_int32(0)
     rc = lib.wm_get_stage_profile(model._handle, buf, cap, C.byref(n))
     assert rc == 0, lib.wm_last_error(model._handle)
-    rows = np.frombuffer(buf, dtype=np.int64)[: n.value * 7].reshape(-1, 7)
+    rows = np.frombuffer(buf, dtype=np.int64)[: n.value * 11].reshape(-1, 11)
     agg = OrderedDict()
-    for st, mode, layer, b0, w0, b1, w1 in rows:
-        a = agg.setdefault((STAGES[st], MODES[mode]), [0, 0, 0, 0, 0])
+    for st, mode, layer, b0, w0, b1, w1, p0, p1, p2, p3 in rows:
+        a = agg.setdefault((STAGES[st], MODES[mode]), [0, 0, 0, 0, 0, 0, 0, 0, 0])
         a[0] += 1; a[1] += b0; a[2] += w0; a[3] += b1; a[4] += w1
+        a[5] += max(p0, 0); a[6] += max(p1, 0); a[7] += max(p2, 0); a[8] += max(p3, 0)
     print(f"{preset} K={heads} iterations={tr.iterations} decode {tr.ms_decode:.3f} ms "
           f"({tr.ms_decode / max(1, tr.iterations):.3f} ms/iter), encoder {tr.ms_encoder:.3f} ms, mel {tr.ms_mel:.3f} ms")
-    print(f"{'stage':<14}{'mode':<6}{'n':>4}{'body0 us':>10}{'wait0 us':>10}{'bodyN us':>10}{'waitN us':>10}{'total us':>10}")
+    print(f"{'stage':<14}{'mode':<6}{'n':>4}{'body0 us':>10}{'wait0 us':>10}{'bodyN us':>10}{'waitN us':>10}{'total us':>10}"
+          f"{'x-staged':>10}{'w-ready':>10}{'mma-done':>10}{'epi-done':>10}")
     tot = 0.0
-    for (st, mode), (cnt, b0, w0, b1, w1) in agg.items():
+    for (st, mode), (cnt, b0, w0, b1, w1, p0, p1, p2, p3) in agg.items():
         t = (b0 + w0) / 1e3
         tot += t
         print(f"{st:<14}{mode:<6}{cnt:>4}{b0 / cnt / 1e3:>10.2f}{w0 / cnt / 1e3:>10.2f}{b1 / cnt / 1e3:>10.2f}"
-              f"{w1 / cnt / 1e3:>10.2f}{t:>10.1f}")
+              f"{w1 / cnt / 1e3:>10.2f}{t:>10.1f}{p0 / cnt / 1e3:>10.2f}{p1 / cnt / 1e3:>10.2f}{p2 / cnt / 1e3:>10.2f}"
+              f"{p3 / cnt / 1e3:>10.2f}")
     print(f"sum over stages of the last iteration (CTA 0): {tot / 1e3:.3f} ms")
     model.close()
 

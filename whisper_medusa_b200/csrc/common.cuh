@@ -158,6 +158,10 @@ struct DecModel {
   float* carry;    // [d] final-LN hidden state of the newest cached token (input of the heads)
   float* cross_part;  // [H][WM_CROSS_CHUNKS][WM_MAX_T][WM_HEAD_DIM + 2]
   unsigned int* cross_cnt;  // [H] arrival counters of the cross-attention chunks (last arriver combines)
+  float* gemm_part;   // [8 k-segments][WM_MAX_T][d] partial sums of K-split GEMM stages (FC2)
+  unsigned int* gemm_cnt;  // [n_sm] arrival counters of their row blocks (last arriver folds)
+  float* sel_part;    // [WM_MAX_T][32 segments][4] partials of the logits scan
+  int sel_nseg;       // vocabulary segments per row of the logits scan: clamp(n_sm / (K+1), 1, 32)
   float* logits_a;    // [WM_MAX_T, V]
   float* logits_b;    // [WM_MAX_T, V]
   // stage program of the persistent ring kernel: {stage, mode, layer} triples; lists [off[i], off[i+1])

@@ -51,8 +51,8 @@ __device__ __forceinline__ PassGeom pass_geom(const DecModel* m, int mode) {
 // -----------------------------------------------------------------------------------------
 // stage: token + position embedding  (HF modeling_whisper.py:737-763)
 // -----------------------------------------------------------------------------------------
-__device__ void stage_embed(const DecModel* m, int mode, int cta, int ncta) {
-  PassGeom g = pass_geom(m, mode);
+__device__ void stage_embed(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
+  const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const DecState* st = m->st;
   const int d = m->d;
   for (int t = cta; t < g.T; t += ncta) {
@@ -313,8 +313,8 @@ __device__ void stage_gemm(const GemmDesc& g, int cta, int ncta, unsigned char* 
 // stage: causal self-attention over the fp16 cache (HF modeling_whisper.py:284-357, T_q <= 16)
 // item = (head, query row); keys 0 .. base + t
 // -----------------------------------------------------------------------------------------
-__device__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw) {
-  PassGeom g = pass_geom(m, mode);
+__device__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
+  const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const int d = m->d, H = m->H;
   const DecLayer& L = m->layers[layer];
   float* s_q = reinterpret_cast<float*>(smem_raw);            // [64]
@@ -405,8 +405,8 @@ __host__ __device__ inline size_t cross_attn_smem_bytes() {
          (size_t)WM_MAX_T * WM_CH_MAX * sizeof(float) + (size_t)WM_MAX_T * 64 * sizeof(float) +
          (size_t)2 * WM_MAX_T * sizeof(float);
 }
-__device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw) {
-  PassGeom g = pass_geom(m, mode);
+__device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
+  const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const int d = m->d, H = m->H, S = m->S;
   const DecLayer& L = m->layers[layer];
   const int CH = (S + WM_CROSS_CHUNKS - 1) / WM_CROSS_CHUNKS;
@@ -535,30 +535,53 @@ __device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta
 //            input of the Medusa heads).  sweep B + block type: base logits read the hidden
 //            states directly (reference model.py:1287).
 // -----------------------------------------------------------------------------------------
-__device__ void stage_final_ln(const DecModel* m, int mode, int cta, int ncta) {
-  PassGeom g = pass_geom(m, mode);
+__device__ void stage_final_ln(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
+  const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const int d = m->d;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (WM_DEC_THREADS >> 5);
-  for (int t = cta * nwarps + warp; t < g.T; t += ncta * nwarps) {
-    const float* x = m->x + (size_t)t * d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = d >> 7;   // float4 per lane (d <= 1280)
+  // one row per CTA (warp 0): the rows are few, spreading them keeps each on its own SM
+  for (int t = cta; t < g.T; t += ncta) {
+    if (warp != 0) continue;
+    const float4* x4 = reinterpret_cast<const float4*>(m->x + (size_t)t * d);
+    float4 v[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+      if (i < nv) v[i] = x4[i * 32 + lane];
     float s = 0.f;
-    for (int j = lane; j < d; j += 32) s += x[j];
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+      if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(s) / (float)d;
-    float v = 0.f;
-    for (int j = lane; j < d; j += 32) { float dl = x[j] - mean; v += dl * dl; }
-    const float rstd = rsqrtf(warp_sum(v) / (float)d + 1e-5f);
-    float* hid = m->hidden + (size_t)t * d;
-    for (int j = lane; j < d; j += 32) {
-      const float y = (x[j] - mean) * rstd * m->lnf_g[j] + m->lnf_b[j];
-      hid[j] = y;
-      if (mode == MODE_A && t == g.T - 1) m->carry[j] = y;
-      if (mode == MODE_B && m->has_block) m->head_h[(size_t)t * d + j] = y;
-    }
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+      if (i < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + e * e);
+      }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+    const float4* g4 = reinterpret_cast<const float4*>(m->lnf_g);
+    const float4* b4 = reinterpret_cast<const float4*>(m->lnf_b);
+    float4* hid = reinterpret_cast<float4*>(m->hidden + (size_t)t * d);
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+      if (i < nv) {
+        const float4 gg = g4[i * 32 + lane], bb = b4[i * 32 + lane];
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * gg.x + bb.x;
+        y.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+        y.z = (v[i].z - mean) * rstd * gg.z + bb.z;
+        y.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+        hid[i * 32 + lane] = y;
+        if (mode == MODE_A && t == g.T - 1) reinterpret_cast<float4*>(m->carry)[i * 32 + lane] = y;
+        if (mode == MODE_B && m->has_block) reinterpret_cast<float4*>(m->head_h + (size_t)t * d)[i * 32 + lane] = y;
+      }
   }
 }
 // block type: the extra layer consumes the LayerNorm'ed hidden states (reference model.py:1374-1376)
-__device__ void stage_copy_hidden_to_x(const DecModel* m, int mode, int cta, int ncta) {
-  PassGeom g = pass_geom(m, mode);
+__device__ void stage_copy_hidden_to_x(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
+  const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const int total = g.T * m->d;
   for (int idx = cta * WM_DEC_THREADS + threadIdx.x; idx < total; idx += ncta * WM_DEC_THREADS) m->x[idx] = m->hidden[idx];
 }
@@ -614,8 +637,19 @@ __device__ float block_sum(float v, float* s_val) {
   return s;
 }
 
-__device__ void stage_select(const DecModel* m, int mode, int cta, int ncta, unsigned char* smem_raw) {
-  DecState* st = m->st;
+// The logits scan is spread over the whole grid: every row is cut into `nseg` vocabulary segments.
+//   SELECT1: per (row, segment): processed max / first argmax / sum of exp relative to the local max
+//   SELECT2 (verify only): with the row max M and normaliser Z folded from the partials, the entropy
+//            term sum p log(p + 1e-5) of the segment and the candidate's probability
+//   SELECT_FIN (tail) / ACCEPT (verify): fold the partials in segment order (deterministic).
+#define WM_SEL_MAXSEG 32
+// the segment count is a property of the model/device (set by the host from the SM count), NOT of the
+// launch: the fold stages run on one CTA and must agree with the scan stages
+__device__ __forceinline__ int select_nseg(const DecModel* m, int /*ncta*/) { return m->sel_nseg; }
+// sel_part layout: [row][seg][4] = {max, argmax (int bits), sumexp, entropy term}
+
+__device__ void stage_select1(const DecModel* m, int mode, int cta, int ncta, unsigned char* smem_raw) {
+  const DecState* st = m->st;
   const int V = m->V, K = m->K;
   float* s_val = reinterpret_cast<float*>(smem_raw);
   int* s_idx = reinterpret_cast<int*>(s_val + 32);
@@ -623,43 +657,93 @@ __device__ void stage_select(const DecModel* m, int mode, int cta, int ncta, uns
   const bool begin_on = (L == st->begin_index);
   const float pen = m->pen_tab[L];
   const int eos = st->eos;
-  const float* logits = (mode == 0) ? m->logits_a : m->logits_b;
-  for (int r = cta; r <= K; r += ncta) {
+  const float* logits = (mode == MODE_A) ? m->logits_a : m->logits_b;
+  const int nseg = select_nseg(m, ncta);
+  const int seglen = (V + nseg - 1) / nseg;
+  const float temp = st->temperature;
+  const float inv_t = temp > 0.f ? 1.0f / temp : 1.0f;
+  for (int item = cta; item < (K + 1) * nseg; item += ncta) {
+    const int r = item / nseg, sg = item - r * nseg;
+    const int j0 = sg * seglen, j1 = min(V, j0 + seglen);
     const float* row = logits + (size_t)r * V;
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int j = threadIdx.x; j < V; j += WM_DEC_THREADS) {
-      float v = processed_logit(row, j, m->tok_mask, begin_on, eos, pen);
+    for (int j = j0 + threadIdx.x; j < j1; j += WM_DEC_THREADS) {
+      const float v = processed_logit(row, j, m->tok_mask, begin_on, eos, pen);
       if (v > bv) { bv = v; bi = j; }   // ascending j per thread => first maximum kept
     }
-    if (bi == 0x7fffffff) bi = threadIdx.x < V ? threadIdx.x : 0;
     block_argmax(bv, bi, s_val, s_idx);
-    if (mode == 0) {
-      if (threadIdx.x == 0) st->cand[r] = bi;
-      continue;
-    }
-    if (threadIdx.x == 0) st->row_argmax[r] = bi;
-    if (r >= K) continue;   // evaluate_posterior reads logits[:, :-1]
-    const float temp = st->temperature;
-    if (temp == 0.f) continue;
-    const float inv_t = 1.0f / temp;
-    const float mx = bv * inv_t;   // max of the temperature-scaled row (temp > 0)
     float z = 0.f;
-    for (int j = threadIdx.x; j < V; j += WM_DEC_THREADS)
-      z += expf(processed_logit(row, j, m->tok_mask, begin_on, eos, pen) * inv_t - mx);
-    z = block_sum(z, s_val);
+    if (mode == MODE_B && r < K && temp > 0.f && bv > -INFINITY) {
+      for (int j = j0 + threadIdx.x; j < j1; j += WM_DEC_THREADS)
+        z += expf((processed_logit(row, j, m->tok_mask, begin_on, eos, pen) - bv) * inv_t);
+      z = block_sum(z, s_val);
+    }
+    if (threadIdx.x == 0) {
+      float* o = m->sel_part + ((size_t)r * WM_SEL_MAXSEG + sg) * 4;
+      o[0] = bv; o[1] = __int_as_float(bi); o[2] = z;
+    }
+  }
+}
+
+// fold the segment partials of row r: global max (first index on ties) and normaliser
+__device__ __forceinline__ void select_fold(const DecModel* m, int r, int nseg, float inv_t, float& M, int& idx, float& Z) {
+  const float* p = m->sel_part + (size_t)r * WM_SEL_MAXSEG * 4;
+  M = -INFINITY; idx = 0x7fffffff;
+  for (int sg = 0; sg < nseg; ++sg) {
+    const float v = __ldcg(p + sg * 4);
+    const int i = __float_as_int(__ldcg(p + sg * 4 + 1));
+    if (v > M || (v == M && i < idx)) { M = v; idx = i; }
+  }
+  Z = 0.f;
+  for (int sg = 0; sg < nseg; ++sg) {
+    const float v = __ldcg(p + sg * 4);
+    if (v > -INFINITY) Z += __ldcg(p + sg * 4 + 2) * expf((v - M) * inv_t);
+  }
+}
+
+__device__ void stage_select2(const DecModel* m, int cta, int ncta, unsigned char* smem_raw) {
+  DecState* st = m->st;
+  const int V = m->V, K = m->K;
+  float* s_val = reinterpret_cast<float*>(smem_raw);
+  const float temp = st->temperature;
+  if (temp == 0.f) return;   // exact-match acceptance needs only the argmax (uniform across the grid)
+  const float inv_t = 1.0f / temp;
+  const int L = st->L;
+  const bool begin_on = (L == st->begin_index);
+  const float pen = m->pen_tab[L];
+  const int eos = st->eos;
+  const int nseg = select_nseg(m, ncta);
+  const int seglen = (V + nseg - 1) / nseg;
+  for (int item = cta; item < K * nseg; item += ncta) {   // evaluate_posterior reads logits[:, :-1]
+    const int r = item / nseg, sg = item - r * nseg;
+    const int j0 = sg * seglen, j1 = min(V, j0 + seglen);
+    const float* row = m->logits_b + (size_t)r * V;
+    float M, Z; int idx;
+    select_fold(m, r, nseg, inv_t, M, idx, Z);
     float ent = 0.f;
-    for (int j = threadIdx.x; j < V; j += WM_DEC_THREADS) {
-      float p = expf(processed_logit(row, j, m->tok_mask, begin_on, eos, pen) * inv_t - mx) / z;
+    for (int j = j0 + threadIdx.x; j < j1; j += WM_DEC_THREADS) {
+      const float p = expf((processed_logit(row, j, m->tok_mask, begin_on, eos, pen) - M) * inv_t) / Z;
       ent += p * logf(p + 1e-5f);
     }
-    ent = -block_sum(ent, s_val);
+    ent = block_sum(ent, s_val);
     if (threadIdx.x == 0) {
+      m->sel_part[((size_t)r * WM_SEL_MAXSEG + sg) * 4 + 3] = ent;
       const int c = st->cand[r + 1];
-      const float pc = expf(processed_logit(row, c, m->tok_mask, begin_on, eos, pen) * inv_t - mx) / z;
-      st->row_pc[r] = pc;
-      st->row_thr[r] = fminf(st->post_thr, expf(-ent) * st->post_alpha);
+      if (c >= j0 && c < j1)
+        st->row_pc[r] = expf((processed_logit(row, c, m->tok_mask, begin_on, eos, pen) - M) * inv_t) / Z;
     }
+  }
+}
+
+// tail: candidates = top-1 of every head row (generate_candidates, medusa_utils.py:446-457)
+__device__ void stage_select_fin(const DecModel* m, int ncta) {
+  DecState* st = m->st;
+  const int nseg = select_nseg(m, ncta);
+  if (threadIdx.x <= m->K) {
+    float M, Z; int idx;
+    select_fold(m, threadIdx.x, nseg, 1.0f, M, idx, Z);
+    st->cand[threadIdx.x] = idx;
   }
 }
 
@@ -677,10 +761,25 @@ __device__ void stage_select(const DecModel* m, int mode, int cta, int ncta, uns
 //   accept-0 iteration (second emitted token = argmax of the verify row, never seen by the
 //   decoder) a one-token sweep A is needed (`need_a`).
 // -----------------------------------------------------------------------------------------
-__device__ void stage_accept(const DecModel* m) {
+__device__ void stage_accept(const DecModel* m, int ncta) {
   __shared__ int s_a;
   DecState* st = m->st;
   const int K = m->K;
+  const int nseg = select_nseg(m, ncta);
+  // fold the scan partials: argmax of every row, acceptance threshold of rows < K
+  if (threadIdx.x <= K) {
+    const int r = threadIdx.x;
+    const float temp = st->temperature;
+    float M, Z; int idx;
+    select_fold(m, r, nseg, temp > 0.f ? 1.0f / temp : 1.0f, M, idx, Z);
+    st->row_argmax[r] = idx;
+    if (r < K && temp > 0.f) {
+      float ent = 0.f;
+      for (int sg = 0; sg < nseg; ++sg) ent += __ldcg(m->sel_part + ((size_t)r * WM_SEL_MAXSEG + sg) * 4 + 3);
+      st->row_thr[r] = fminf(st->post_thr, expf(ent) * st->post_alpha);   // ent = sum p log(p+1e-5) = -entropy
+    }
+  }
+  cta_sync();
   if (threadIdx.x == 0) {
     const int L = st->L;
     int a = 0;
@@ -719,12 +818,13 @@ __device__ void stage_accept(const DecModel* m) {
 // -----------------------------------------------------------------------------------------
 enum StageId {
   ST_EMBED = 0, ST_QKV, ST_SELF_ATTN, ST_OPROJ, ST_CROSS_Q, ST_CROSS_ATTN, ST_CROSS_O,
-  ST_FC1, ST_FC2, ST_FINAL_LN, ST_COPY_HIDDEN, ST_TAIL_SEED, ST_HEADS, ST_VOCAB, ST_SELECT, ST_ACCEPT
+  ST_FC1, ST_FC2, ST_FINAL_LN, ST_COPY_HIDDEN, ST_TAIL_SEED, ST_HEADS, ST_VOCAB, ST_SELECT1, ST_SELECT2, ST_SELECT_FIN,
+  ST_ACCEPT
 };
 enum PhaseId { PH_SWEEP_A = 0, PH_TAIL = 1, PH_VERIFY = 2 };
 
-__device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mode, int layer) {
-  PassGeom pg = pass_geom(m, mode);
+__device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mode, int layer, const PassGeom* gopt) {
+  const PassGeom pg = gopt ? *gopt : pass_geom(m, mode);
   GemmDesc g;
   const int d = m->d;
   g.d = d;
@@ -791,18 +891,21 @@ __device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mode, int l
   return g;
 }
 
-__device__ void run_stage(const DecModel* m, int stage, int mode, int layer, int cta, int ncta, unsigned char* smem) {
+__device__ void run_stage(const DecModel* m, int stage, int mode, int layer, int cta, int ncta, unsigned char* smem,
+                          const PassGeom* gopt = nullptr) {
   switch (stage) {
-    case ST_EMBED: stage_embed(m, mode, cta, ncta); break;
-    case ST_SELF_ATTN: stage_self_attn(m, mode, layer, cta, ncta, smem); break;
-    case ST_CROSS_ATTN: stage_cross_attn(m, mode, layer, cta, ncta, smem); break;
-    case ST_FINAL_LN: stage_final_ln(m, mode, cta, ncta); break;
-    case ST_COPY_HIDDEN: stage_copy_hidden_to_x(m, mode, cta, ncta); break;
+    case ST_EMBED: stage_embed(m, mode, cta, ncta, gopt); break;
+    case ST_SELF_ATTN: stage_self_attn(m, mode, layer, cta, ncta, smem, gopt); break;
+    case ST_CROSS_ATTN: stage_cross_attn(m, mode, layer, cta, ncta, smem, gopt); break;
+    case ST_FINAL_LN: stage_final_ln(m, mode, cta, ncta, gopt); break;
+    case ST_COPY_HIDDEN: stage_copy_hidden_to_x(m, mode, cta, ncta, gopt); break;
     case ST_TAIL_SEED: stage_tail_seed(m, cta, ncta); break;
-    case ST_SELECT: stage_select(m, mode, cta, ncta, smem); break;
-    case ST_ACCEPT: if (cta == 0) stage_accept(m); break;
+    case ST_SELECT1: stage_select1(m, mode, cta, ncta, smem); break;
+    case ST_SELECT2: stage_select2(m, cta, ncta, smem); break;
+    case ST_SELECT_FIN: if (cta == 0) stage_select_fin(m, ncta); break;
+    case ST_ACCEPT: if (cta == 0) stage_accept(m, ncta); break;
     default: {
-      GemmDesc g = make_gemm_desc(m, stage, mode, layer);
+      GemmDesc g = make_gemm_desc(m, stage, mode, layer, gopt);
       stage_gemm(g, cta, ncta, smem);
     }
   }
@@ -829,14 +932,14 @@ __host__ __device__ void seq_sweep(int n_layers, int has_block, int mode, F&& f)
 template <class F>
 __host__ __device__ void seq_tail(int n_layers, int has_block, F&& f) {
   if (has_block) { f(ST_TAIL_SEED, MODE_TAIL, 0); seq_layer(n_layers, MODE_TAIL, f); }
-  f(ST_HEADS, MODE_A, 0); f(ST_VOCAB, MODE_A, 0); f(ST_SELECT, MODE_A, 0);
+  f(ST_HEADS, MODE_A, 0); f(ST_VOCAB, MODE_A, 0); f(ST_SELECT1, MODE_A, 0); f(ST_SELECT_FIN, MODE_A, 0);
 }
 // verify: sweep B, base logits of the K+1 positions, acceptance statistics, accept
 template <class F>
 __host__ __device__ void seq_verify(int n_layers, int has_block, F&& f) {
   seq_sweep(n_layers, has_block, MODE_B, f);
   if (!has_block) f(ST_HEADS, MODE_B, 0);
-  f(ST_VOCAB, MODE_B, 0); f(ST_SELECT, MODE_B, 0); f(ST_ACCEPT, MODE_B, 0);
+  f(ST_VOCAB, MODE_B, 0); f(ST_SELECT1, MODE_B, 0); f(ST_SELECT2, MODE_B, 0); f(ST_ACCEPT, MODE_B, 0);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -918,7 +1021,7 @@ void dec_build_program(int n_layers, int has_block, std::vector<int>& flat, int 
 size_t dec_ring_smem_bytes(int d) { return ring_smem_bytes(d); }
 
 // Per-CTA chunk schedule of the ring producer, in exactly the order stage_gemm_ring consumes:
-// for every GEMM stage of the program with rows for the CTA: for seg (K / d): for unit (16 rows).
+// for every GEMM stage of the program with work for the CTA (gemm_work): for unit (16 rows).
 // `hm` is the HOST copy of the model (device pointers inside).  off has 4 entries per CTA.
 void dec_build_chunk_table(const DecModel& hm, int ncta, std::vector<ChunkDesc>& tab, std::vector<int>& off) {
   std::vector<int> flat;
@@ -933,18 +1036,16 @@ void dec_build_chunk_table(const DecModel& hm, int ncta, std::vector<ChunkDesc>&
         const int stage = flat[ip * 3], mode = flat[ip * 3 + 1], layer = flat[ip * 3 + 2];
         if (!is_gemm_stage(stage)) continue;
         const WDesc w = stage_weights(&hm, stage, mode, layer);
-        int nb, nr;
-        cta_rows(w.N, cta, ncta, nb, nr);
-        if (nr == 0) continue;
-        const int units = (nr + 15) >> 4, segs = w.K / hm.d;
-        for (int sg = 0; sg < segs; ++sg)
-          for (int u = 0; u < units; ++u) {
-            ChunkDesc c;
-            c.src = w.W + (size_t)(nb + u * 16) * w.K + (size_t)sg * hm.d;
-            c.row_bytes = (uint32_t)(w.K * sizeof(__half));
-            c.nrows = (uint32_t)std::min(16, nr - u * 16);
-            tab.push_back(c);
-          }
+        const GemmWork wk = gemm_work(w.N, w.K, hm.d, cta, ncta);
+        if (wk.n_rows == 0) continue;
+        const int units = (wk.n_rows + 15) >> 4;
+        for (int u = 0; u < units; ++u) {
+          ChunkDesc c;
+          c.src = w.W + (size_t)(wk.n_begin + u * 16) * w.K + (size_t)wk.seg * hm.d;
+          c.row_bytes = (uint32_t)(w.K * sizeof(__half));
+          c.nrows = (uint32_t)std::min(16, wk.n_rows - u * 16);
+          tab.push_back(c);
+        }
       }
     }
     off[(size_t)cta * 4 + 3] = (int)tab.size();
@@ -982,7 +1083,7 @@ static int stage_grid(int stage, int T, int n_sm, int H, int K) {
     case ST_FINAL_LN: return 1;
     case ST_COPY_HIDDEN: return 8;
     case ST_TAIL_SEED: return 2;
-    case ST_SELECT: return K + 1;
+    case ST_SELECT_FIN: return 1;
     case ST_ACCEPT: return 1;
     default: return n_sm;
   }

@@ -10,10 +10,18 @@
 // in the grid barrier of stage s.  When a stage's activations finally arrive, its weights are
 // already on-chip and the stage costs: X staging (L2) + a few MMAs out of shared memory + epilogue.
 //
-// Roles: warps 0..15 = compute (WM_DEC_THREADS threads, named barrier 1), warp 16 = producer.
+// Roles: warps 0..14 = compute (WM_DEC_THREADS threads, named barrier 1), warp 15 = producer.
 // The producer walks a per-CTA chunk table that the host builds once per model (no pointer
 // chasing on the device), waits on `empty[slot]`, arms `full[slot]` with the byte count and lets
 // lanes 0..nrows-1 issue one bulk copy per weight row.
+//
+// Control data never waits on L2 after a barrier (every grid barrier invalidates L1): the model
+// description lives in a shared-memory copy, the pass geometry in registers, and the next stage
+// instruction is loaded before the barrier it follows.
+//
+// Stages with K > d (FC2) are split over CTAs along K as well: CTA = (row block, k segment); the
+// segment partials go to a global scratch and the CTA that arrives last for a row block folds
+// them in segment order (deterministic) and runs the epilogue.
 //
 // Ring geometry: a "chunk" = up to 16 weight rows x d columns (fp16), row stride d*2 + 64 B
 // (bank-conflict-free LDS.128 of the B fragments); WM_RING_G chunks are resident; chunks are
@@ -58,6 +66,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __host__ __device__ __forceinline__ bool is_gemm_stage(int st) {
   return st == ST_QKV || st == ST_OPROJ || st == ST_CROSS_Q || st == ST_CROSS_O || st == ST_FC1 || st == ST_FC2 ||
@@ -86,10 +95,29 @@ __host__ __device__ inline WDesc stage_weights(const DecModel* m, int stage, int
   return w;
 }
 
-__host__ __device__ __forceinline__ void cta_rows(int N, int cta, int ncta, int& n_begin, int& n_rows) {
-  const int rows_per = N / ncta, rem = N % ncta;
-  n_begin = cta * rows_per + (cta < rem ? cta : rem);
-  n_rows = rows_per + (cta < rem ? 1 : 0);
+__host__ __device__ __forceinline__ void cta_rows(int N, int part, int nparts, int& n_begin, int& n_rows) {
+  const int rows_per = N / nparts, rem = N % nparts;
+  n_begin = part * rows_per + (part < rem ? part : rem);
+  n_rows = rows_per + (part < rem ? 1 : 0);
+}
+
+// Work of one CTA in a GEMM stage: rows [n_begin, n_begin + n_rows) of W, k segment `seg` of `segs`
+// (segs > 1 <=> K > d: the stage is split along K over CTAs; `block` = row block shared by `segs` CTAs).
+struct GemmWork { int n_begin, n_rows, seg, segs, block; };
+__host__ __device__ __forceinline__ GemmWork gemm_work(int N, int K, int d, int cta, int ncta) {
+  GemmWork w;
+  w.segs = K / d;
+  if (w.segs <= 1) {
+    w.segs = 1; w.seg = 0; w.block = cta;
+    cta_rows(N, cta, ncta, w.n_begin, w.n_rows);
+    return w;
+  }
+  const int nb = ncta / w.segs;   // host guarantees nb >= 1
+  if (cta >= nb * w.segs) { w.n_begin = 0; w.n_rows = 0; w.seg = 0; w.block = 0; return w; }
+  w.block = cta / w.segs;
+  w.seg = cta - w.block * w.segs;
+  cta_rows(N, w.block, nb, w.n_begin, w.n_rows);
+  return w;
 }
 
 struct RingCtx {
@@ -108,11 +136,14 @@ struct RingCtx {
 // ---------------------------------------------------------------------------------------------
 __device__ void ring_producer(const RingCtx& rc, const ChunkDesc* __restrict__ tab, int first, int last) {
   const int lane = threadIdx.x & 31;
+  if (first >= last) return;
+  ChunkDesc nxt = tab[first];
   for (int c = first; c < last; ++c) {
     const unsigned int k = (unsigned int)(c - first);
     const int slot = k % WM_RING_G;
     const unsigned int round = k / WM_RING_G;
-    const ChunkDesc dsc = tab[c];                       // same address on every lane: one broadcast load
+    const ChunkDesc dsc = nxt;
+    if (c + 1 < last) nxt = tab[c + 1];                 // next descriptor is in flight while we wait
     if (lane == 0) {
       while (!mbar_try_wait(rc.empty + slot, (round & 1) ^ 1)) { }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the slot vs async writes
@@ -148,16 +179,16 @@ __device__ __forceinline__ void store_hilo4(__half* hi, __half* lo, float4 y) {
 __device__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __half* xlo, int xstride, int& rows_dirty) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = WM_DEC_THREADS >> 5;
   const int T = g.x_rows;
-  // rows that still hold data of an earlier, taller stage must read as zero
-  if (rows_dirty > T) {
-    const int n16 = (rows_dirty - T) * xstride / 8;   // uint4 = 8 halfs; xstride % 8 == 0
-    uint4* zh = reinterpret_cast<uint4*>(xhi + (size_t)T * xstride);
-    uint4* zl = reinterpret_cast<uint4*>(xlo + (size_t)T * xstride);
-    for (int i = tid; i < n16; i += WM_DEC_THREADS) { zh[i] = make_uint4(0, 0, 0, 0); zl[i] = make_uint4(0, 0, 0, 0); }
-  }
-  rows_dirty = T;
   if (g.xsrc == XS_LN) {
     const int nv = d >> 7;   // float4 per lane
+    const float4* g4 = reinterpret_cast<const float4*>(g.ln_g);
+    const float4* b4 = reinterpret_cast<const float4*>(g.ln_b);
+    if (warp < T) {
+      // the affine parameters are only needed after two reductions: pull them into L1 meanwhile
+#pragma unroll
+      for (int i = 0; i < WM_LN_MAXV; ++i)
+        if (i < nv) { prefetch_l1(g4 + i * 32 + lane); prefetch_l1(b4 + i * 32 + lane); }
+    }
     for (int r = warp; r < T; r += nwarps) {
       const float4* x4 = reinterpret_cast<const float4*>(g.X + (size_t)(g.x_row0 + r) * d);
       float4 v[WM_LN_MAXV];
@@ -177,8 +208,6 @@ __device__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __h
           q += (a * a + b * b) + (c * c + e * e);
         }
       const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
-      const float4* g4 = reinterpret_cast<const float4*>(g.ln_g);
-      const float4* b4 = reinterpret_cast<const float4*>(g.ln_b);
 #pragma unroll
       for (int i = 0; i < WM_LN_MAXV; ++i)
         if (i < nv) {
@@ -215,88 +244,127 @@ __device__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __h
       }
     }
   }
+  // rows that still hold data of an earlier, taller stage must read as zero
+  if (rows_dirty > T) {
+    const int n16 = (rows_dirty - T) * xstride / 8;   // uint4 = 8 halfs; xstride % 8 == 0
+    uint4* zh = reinterpret_cast<uint4*>(xhi + (size_t)T * xstride);
+    uint4* zl = reinterpret_cast<uint4*>(xlo + (size_t)T * xstride);
+    for (int i = tid; i < n16; i += WM_DEC_THREADS) { zh[i] = make_uint4(0, 0, 0, 0); zl[i] = make_uint4(0, 0, 0, 0); }
+  }
+  rows_dirty = T;
 }
 
 // ---------------------------------------------------------------------------------------------
 // GEMM stage fed from the ring (compute warps)
 // ---------------------------------------------------------------------------------------------
-__device__ void stage_gemm_ring(RingCtx& rc, const GemmDesc& g, __half* xhi, __half* xlo, float* partial, int& rows_dirty) {
+__device__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, const GemmDesc& g, __half* xhi, __half* xlo, float* partial,
+                                int& rows_dirty, unsigned long long* pr) {
+  __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
   const int d = rc.d;
   const int xstride = d + WM_XPAD;
-  int n_begin, n_rows;
-  cta_rows(g.N, rc.cta, rc.ncta, n_begin, n_rows);
-  if (n_rows == 0) return;   // the chunk table has no entry for such stages either
+  const GemmWork wk = gemm_work(g.N, g.K, d, rc.cta, rc.ncta);
+  if (wk.n_rows == 0) return;   // the chunk table has no entry for such stages either
+  const int n_begin = wk.n_begin, n_rows = wk.n_rows;
   const int units = (n_rows + 15) >> 4;
-  const int segs = g.K / d;
   int nks = 8;               // k-slices per chunk: one warp each, both n8 tiles of the chunk
   while ((d / nks) % 32 != 0) nks >>= 1;
   const int KS = d / nks;
   const int T = g.x_rows;
   const int rs_h = rc.row_stride / 2;   // ring row stride in halfs
-  float racc = 0.f;                      // multi-segment accumulator of output element `tid` (units == 1 when segs > 1)
+  const bool ksplit = wk.segs > 1;
 
-  for (int sg = 0; sg < segs; ++sg) {
-    if (sg > 0) cta_sync();
-    ring_stage_x(g, sg, d, xhi, xlo, xstride, rows_dirty);
-    cta_sync();
-    for (int u = 0; u < units; ++u) {
-      const unsigned int c = rc.consumed;
-      const int slot = c % WM_RING_G;
-      const int nvalid = min(16, n_rows - u * 16);
-      while (!mbar_try_wait(rc.full + slot, (c / WM_RING_G) & 1)) { }
-      if (warp < nks) {
-        const __half* sl = reinterpret_cast<const __half*>(rc.ring + (size_t)slot * rc.slot_bytes);
-        const bool v0 = gq < nvalid, v1 = (gq + 8) < nvalid;
-        const __half* w0p = sl + (size_t)gq * rs_h + warp * KS + 8 * tq;
-        const __half* w1p = sl + (size_t)(gq + 8) * rs_h + warp * KS + 8 * tq;
-        const __half* xh0 = xhi + (size_t)gq * xstride + warp * KS + 8 * tq;
-        const __half* xh1 = xh0 + 8 * xstride;
-        const __half* xl0 = xlo + (size_t)gq * xstride + warp * KS + 8 * tq;
-        const __half* xl1 = xl0 + 8 * xstride;
-        const bool t1 = (gq + 8) < T;   // token rows 8..15 are zero when T <= 8 + gq
-        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint4 z = make_uint4(0, 0, 0, 0);
+  ring_stage_x(g, wk.seg, d, xhi, xlo, xstride, rows_dirty);
+  // output element owned by this thread in the fold below
+  const int e_ = tid >> 5, ln_ = tid & 31;
+  const int j_ = (e_ >> 2) & 1, i_ = e_ & 3;
+  const int token = (ln_ >> 2) + ((i_ >= 2) ? 8 : 0);
+  const int rloc = j_ * 8 + 2 * (ln_ & 3) + (i_ & 1);
+  // residual epilogue: fetch the old value while the MMAs run (single-unit stages only)
+  float old = 0.f;
+  const bool pre_old = (g.epi == EPI_RESID) && !ksplit && units == 1 && tid < 256 && token < T && rloc < n_rows;
+  if (pre_old) old = g.out[(size_t)token * g.ldo + n_begin + rloc];
+  cta_sync();
+  if (pr) pr[3] = global_timer_ns();
+  for (int u = 0; u < units; ++u) {
+    const unsigned int c = rc.consumed;
+    const int slot = c % WM_RING_G;
+    const int nvalid = min(16, n_rows - u * 16);
+    while (!mbar_try_wait(rc.full + slot, (c / WM_RING_G) & 1)) { }
+    if (pr && u == 0) pr[4] = global_timer_ns();
+    if (warp < nks) {
+      const __half* sl = reinterpret_cast<const __half*>(rc.ring + (size_t)slot * rc.slot_bytes);
+      const bool v0 = gq < nvalid, v1 = (gq + 8) < nvalid;
+      const __half* w0p = sl + (size_t)gq * rs_h + warp * KS + 8 * tq;
+      const __half* w1p = sl + (size_t)(gq + 8) * rs_h + warp * KS + 8 * tq;
+      const __half* xh0 = xhi + (size_t)gq * xstride + warp * KS + 8 * tq;
+      const __half* xh1 = xh0 + 8 * xstride;
+      const __half* xl0 = xlo + (size_t)gq * xstride + warp * KS + 8 * tq;
+      const __half* xl1 = xl0 + 8 * xstride;
+      const bool t1 = (gq + 8) < T;   // token rows 8..15 are zero when T <= 8 + gq
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll 5
-        for (int kk = 0; kk < KS; kk += 32) {
-          const uint4 wa = v0 ? *reinterpret_cast<const uint4*>(w0p + kk) : z;
-          const uint4 wb = v1 ? *reinterpret_cast<const uint4*>(w1p + kk) : z;
-          const uint4 ah0 = *reinterpret_cast<const uint4*>(xh0 + kk);
-          const uint4 al0 = *reinterpret_cast<const uint4*>(xl0 + kk);
-          const uint4 ah1 = t1 ? *reinterpret_cast<const uint4*>(xh1 + kk) : z;
-          const uint4 al1 = t1 ? *reinterpret_cast<const uint4*>(xl1 + kk) : z;
-          mma_16816(c0, ah0.x, ah1.x, ah0.y, ah1.y, wa.x, wa.y);
-          mma_16816(c0, ah0.z, ah1.z, ah0.w, ah1.w, wa.z, wa.w);
-          mma_16816(c0, al0.x, al1.x, al0.y, al1.y, wa.x, wa.y);
-          mma_16816(c0, al0.z, al1.z, al0.w, al1.w, wa.z, wa.w);
-          mma_16816(c1, ah0.x, ah1.x, ah0.y, ah1.y, wb.x, wb.y);
-          mma_16816(c1, ah0.z, ah1.z, ah0.w, ah1.w, wb.z, wb.w);
-          mma_16816(c1, al0.x, al1.x, al0.y, al1.y, wb.x, wb.y);
-          mma_16816(c1, al0.z, al1.z, al0.w, al1.w, wb.z, wb.w);
-        }
+      for (int kk = 0; kk < KS; kk += 32) {
+        const uint4 wa = v0 ? *reinterpret_cast<const uint4*>(w0p + kk) : z;
+        const uint4 wb = v1 ? *reinterpret_cast<const uint4*>(w1p + kk) : z;
+        const uint4 ah0 = *reinterpret_cast<const uint4*>(xh0 + kk);
+        const uint4 al0 = *reinterpret_cast<const uint4*>(xl0 + kk);
+        const uint4 ah1 = t1 ? *reinterpret_cast<const uint4*>(xh1 + kk) : z;
+        const uint4 al1 = t1 ? *reinterpret_cast<const uint4*>(xl1 + kk) : z;
+        mma_16816(c0, ah0.x, ah1.x, ah0.y, ah1.y, wa.x, wa.y);
+        mma_16816(c0, ah0.z, ah1.z, ah0.w, ah1.w, wa.z, wa.w);
+        mma_16816(c0, al0.x, al1.x, al0.y, al1.y, wa.x, wa.y);
+        mma_16816(c0, al0.z, al1.z, al0.w, al1.w, wa.z, wa.w);
+        mma_16816(c1, ah0.x, ah1.x, ah0.y, ah1.y, wb.x, wb.y);
+        mma_16816(c1, ah0.z, ah1.z, ah0.w, ah1.w, wb.z, wb.w);
+        mma_16816(c1, al0.x, al1.x, al0.y, al1.y, wb.x, wb.y);
+        mma_16816(c1, al0.z, al1.z, al0.w, al1.w, wb.z, wb.w);
+      }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          partial[(size_t)warp * 256 + e * 32 + lane] = c0[e];
-          partial[(size_t)warp * 256 + (4 + e) * 32 + lane] = c1[e];
-        }
+      for (int e = 0; e < 4; ++e) {
+        partial[(size_t)warp * 256 + e * 32 + lane] = c0[e];
+        partial[(size_t)warp * 256 + (4 + e) * 32 + lane] = c1[e];
       }
-      cta_sync();   // partials visible; every read of the slot (and of X for this chunk) is done
-      rc.consumed = c + 1;
-      if (tid == 0) mbar_arrive(rc.empty + slot);   // hand the slot back to the producer
-      if (tid < 256) {
-        const int e = tid >> 5, ln = tid & 31;
-        const int j = e >> 2, i = e & 3;
-        const int token = (ln >> 2) + ((i >= 2) ? 8 : 0);
-        const int rloc = j * 8 + 2 * (ln & 3) + (i & 1);
-        if (token < T && rloc < nvalid) {
-          float s = 0.f;
-          for (int ks = 0; ks < nks; ++ks) s += partial[(size_t)ks * 256 + tid];
-          if (segs > 1) { racc += s; s = racc; }
-          if (sg == segs - 1) gemm_epilogue(g, token, n_begin + u * 16 + rloc, s, xhi, xlo, xstride);
-        }
+    }
+    cta_sync();   // partials visible; every read of the slot (and of X for this chunk) is done
+    if (pr && u == 0) pr[5] = global_timer_ns();
+    rc.consumed = c + 1;
+    if (tid == 0) mbar_arrive(rc.empty + slot);   // hand the slot back to the producer
+    if (tid < 256 && token < T && rloc < nvalid) {
+      float s = 0.f;
+      for (int ks = 0; ks < nks; ++ks) s += partial[(size_t)ks * 256 + tid];
+      const int row = n_begin + u * 16 + rloc;
+      if (ksplit) {
+        m->gemm_part[((size_t)wk.seg * 16 + token) * g.N + row] = s;
+      } else if (pre_old) {
+        g.out[(size_t)token * g.ldo + row] = old + (s + (g.bias ? g.bias[row] : 0.f));
+      } else {
+        gemm_epilogue(g, token, row, s, xhi, xlo, xstride);
       }
-      cta_sync();   // partial buffer reusable
+    }
+    cta_sync();   // partial buffer reusable
+    if (pr && u == 0) pr[6] = global_timer_ns();
+  }
+  if (ksplit) {
+    // the last of the `segs` CTAs of this row block folds the segment partials, always in segment order
+    __threadfence();
+    cta_sync();
+    if (tid == 0) {
+      const unsigned int prev = atomicAdd(&m->gemm_cnt[wk.block], 1u);
+      s_last = (prev == (unsigned int)(wk.segs - 1)) ? 1 : 0;
+      if (s_last) m->gemm_cnt[wk.block] = 0u;
+    }
+    cta_sync();
+    if (s_last) {
+      __threadfence();
+      for (int idx = tid; idx < T * n_rows; idx += WM_DEC_THREADS) {
+        const int t = idx / n_rows, row = n_begin + (idx - t * n_rows);
+        float s = 0.f;
+        for (int sg = 0; sg < wk.segs; ++sg) s += __ldcg(m->gemm_part + ((size_t)sg * 16 + t) * g.N + row);
+        gemm_epilogue(g, t, row, s, xhi, xlo, xstride);
+      }
     }
   }
 }
@@ -307,17 +375,19 @@ __host__ __device__ inline size_t ring_scratch_bytes(int d) {
   if (scratch < self_attn_smem_bytes()) scratch = self_attn_smem_bytes();
   return (scratch + 127) / 128 * 128;
 }
+__host__ __device__ inline size_t ring_model_bytes() { return (sizeof(DecModel) + 127) / 128 * 128; }
 __host__ __device__ inline size_t ring_smem_bytes(int d) {
-  return (size_t)WM_RING_G * 16 * (d * 2 + 64) + ring_scratch_bytes(d) + (size_t)8 * 256 * sizeof(float) + 128;
+  return (size_t)WM_RING_G * 16 * (d * 2 + 64) + ring_scratch_bytes(d) + (size_t)8 * 256 * sizeof(float) + ring_model_bytes() + 128;
 }
 
 __global__ void __launch_bounds__(WM_RING_THREADS, 1)
-dec_iteration_ring_kernel(const DecModel* __restrict__ m) {
+dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const DecState* st = m->st;
+  const DecState* st = gm->st;
   if (st->done) return;
   const int need_a = st->need_a;
-  const int d = m->d;
+  const int L0 = st->L, kv0 = st->kv_len;
+  const int d = gm->d;
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int warp = threadIdx.x >> 5;
   RingCtx rc;
@@ -329,7 +399,8 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ m) {
   __half* xhi = reinterpret_cast<__half*>(scratch_p);
   __half* xlo = xhi + 16 * (d + WM_XPAD);
   float* partial = reinterpret_cast<float*>(scratch_p + ring_scratch_bytes(d));
-  rc.full = reinterpret_cast<uint64_t*>(partial + 8 * 256);
+  DecModel* sm = reinterpret_cast<DecModel*>(partial + 8 * 256);   // shared-memory copy of the model description
+  rc.full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sm) + ring_model_bytes());
   rc.empty = rc.full + WM_RING_G;
   rc.cta = cta; rc.ncta = ncta;
   rc.consumed = 0;
@@ -337,7 +408,14 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ m) {
     for (int i = 0; i < WM_RING_G; ++i) { mbar_init(rc.full + i, 1); mbar_init(rc.empty + i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  {
+    const int4* src = reinterpret_cast<const int4*>(gm);
+    int4* dst = reinterpret_cast<int4*>(sm);
+    // (the device copy of DecModel is allocated in 256-byte granules: reading up to the next 16 B is safe)
+    for (int i = threadIdx.x; i < (int)((sizeof(DecModel) + 15) / 16); i += WM_RING_THREADS) dst[i] = src[i];
+  }
   __syncthreads();   // the only full-CTA barrier: after it the producer warp goes its own way
+  const DecModel* m = sm;
 
   if (warp == WM_DEC_THREADS / 32) {
     // ===== producer warp =====
@@ -357,27 +435,41 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ m) {
   int rows_dirty = 0;
   unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(&m->bar[2]);
   unsigned int* bar = m->bar;
+  // pass geometry of this launch (the loop state only changes in the very last stage)
+  PassGeom geom[3];
+  geom[MODE_A].T = L0 - kv0;  geom[MODE_A].base = kv0;
+  geom[MODE_B].T = m->K + 1;  geom[MODE_B].base = L0;
+  geom[MODE_TAIL].T = 1;      geom[MODE_TAIL].base = L0 - 1;
 
-  for (int list = need_a ? 0 : 1; list <= 2; ++list) {
-    const int i0 = m->prog_off[list], i1 = m->prog_off[list + 1];
-    for (int ip = i0; ip < i1; ++ip) {
-      const StageInstr in = m->prog[ip];
-      // optional per-stage timeline (CTA 0 and the last CTA): begin / end of body / end of barrier
-      const bool prof = m->prof != nullptr && threadIdx.x == 0 && (cta == 0 || cta == ncta - 1);
-      unsigned long long* pr = prof ? m->prof + ((size_t)(cta == 0 ? 0 : 1) * m->prog_off[3] + ip) * 3 : nullptr;
-      if (prof) pr[0] = global_timer_ns();
-      if (is_gemm_stage(in.stage)) {
-        GemmDesc g = make_gemm_desc(m, in.stage, in.mode, in.layer);
-        stage_gemm_ring(rc, g, xhi, xlo, partial, rows_dirty);
-      } else {
-        run_stage(m, in.stage, in.mode, in.layer, cta, ncta, scratch_p);
-        // attention stages overlay the activation slice: everything there is dirty now
-        if (in.stage == ST_SELF_ATTN || in.stage == ST_CROSS_ATTN || in.stage == ST_SELECT) rows_dirty = 16;
-      }
-      if (prof) pr[1] = global_timer_ns();
-      grid_barrier(bar, epoch, ncta);
-      if (prof) pr[2] = global_timer_ns();
+  const int ip_first = need_a ? m->prog_off[0] : m->prog_off[1];
+  const int ip_last = m->prog_off[3];
+  StageInstr in = m->prog[ip_first];
+  for (int ip = ip_first; ip < ip_last; ++ip) {
+    // the next instruction is fetched before the barrier of this one: its L2 latency hides there
+    StageInstr nxt = in;
+    if (ip + 1 < ip_last) nxt = m->prog[ip + 1];
+    // optional per-stage timeline (CTA 0 and the last CTA): begin / end of body / end of barrier
+    const bool prof = m->prof != nullptr && threadIdx.x == 0 && (cta == 0 || cta == ncta - 1);
+    unsigned long long* pr = prof ? m->prof + ((size_t)(cta == 0 ? 0 : 1) * m->prog_off[3] + ip) * 8 : nullptr;
+    if (prof) pr[0] = global_timer_ns();
+    PassGeom pgv;
+    if (in.mode == MODE_A) pgv = geom[MODE_A];
+    else if (in.mode == MODE_B) pgv = geom[MODE_B];
+    else pgv = geom[MODE_TAIL];
+    const PassGeom* pg = &pgv;
+    if (is_gemm_stage(in.stage)) {
+      GemmDesc g = make_gemm_desc(m, in.stage, in.mode, in.layer, pg);
+      stage_gemm_ring(rc, m, g, xhi, xlo, partial, rows_dirty, pr);
+    } else {
+      run_stage(m, in.stage, in.mode, in.layer, cta, ncta, scratch_p, pg);
+      // attention / scan stages overlay the activation slice: everything there is dirty now
+      if (in.stage == ST_SELF_ATTN || in.stage == ST_CROSS_ATTN || in.stage == ST_SELECT1 || in.stage == ST_SELECT2)
+        rows_dirty = 16;
     }
+    if (prof) pr[1] = global_timer_ns();
+    grid_barrier(bar, epoch, ncta);
+    if (prof) pr[2] = global_timer_ns();
+    in = nxt;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) m->bar[2] = epoch;
 }

@@ -269,6 +269,13 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   CK(dalloc(&m.carry, d));
   CK(dalloc(&m.cross_part, (size_t)c.n_heads * WM_CROSS_CHUNKS * WM_MAX_T * (WM_HEAD_DIM + 2)));
   CK(dalloc(&m.cross_cnt, (size_t)c.n_heads));
+  if (f % d != 0 || f / d > 8 || h->n_sm < (int)(f / d)) return fail(h, WM_ERR_UNSUPPORTED, "ffn_dim must be a multiple (<= 8x) of d_model");
+  CK(dalloc(&m.gemm_part, (size_t)8 * WM_MAX_T * d));
+  CK(dalloc(&m.gemm_cnt, (size_t)h->n_sm));
+  CK(dalloc(&m.sel_part, (size_t)WM_MAX_T * 32 * 4));
+  m.sel_nseg = h->n_sm / (c.medusa_num_heads + 1);
+  if (m.sel_nseg < 1) m.sel_nseg = 1;
+  if (m.sel_nseg > 32) m.sel_nseg = 32;
   CK(dalloc(&m.logits_a, (size_t)WM_MAX_T * V));
   CK(dalloc(&m.logits_b, (size_t)WM_MAX_T * V));
   CK(dalloc(&h->st, 1));
@@ -317,7 +324,7 @@ extern "C" int wm_destroy(wm_handle* h) {
   for (auto p : h->cross_kv) F(p);
   for (auto p : h->self_k) F(p);
   for (auto p : h->self_v) F(p);
-  F(h->hm.x); F(h->hm.q); F(h->hm.attn); F(h->hm.ffn_h); F(h->hm.hidden); F(h->hm.head_h); F(h->hm.carry); F(h->hm.cross_part); F(h->hm.cross_cnt);
+  F(h->hm.x); F(h->hm.q); F(h->hm.attn); F(h->hm.ffn_h); F(h->hm.hidden); F(h->hm.head_h); F(h->hm.carry); F(h->hm.cross_part); F(h->hm.cross_cnt); F(h->hm.sel_part); F(h->hm.gemm_part); F(h->hm.gemm_cnt);
   F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->prog); F(h->prof); F(h->chunk_tab); F(h->chunk_off); F(h->dm);
   if (h->wowned) F(h->wdev);
   if (h->h_state) cudaFreeHost(h->h_state);
@@ -607,6 +614,7 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
     CK(cudaMemcpyAsync(h->st, &hs, sizeof hs, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(h->bar, 0, 8 * sizeof(unsigned int), s));
     CK(cudaMemsetAsync(h->hm.cross_cnt, 0, (size_t)h->cfg.n_heads * sizeof(unsigned int), s));
+    CK(cudaMemsetAsync(h->hm.gemm_cnt, 0, (size_t)h->n_sm * sizeof(unsigned int), s));
     CK(cudaStreamSynchronize(s));
   }
   cudaGraphExec_t gA1 = nullptr, gAp = nullptr, gT = nullptr, gB = nullptr;
@@ -715,7 +723,7 @@ extern "C" int wm_set_option(wm_handle* h, const char* key, int32_t value) {
   if (k == "profile") {
     // stage timeline of the persistent ring kernel (debug): buffer [2][n_instr][3] u64
     CK(cudaSetDevice(h->device));
-    if (value && !h->prof) CK(dalloc(&h->prof, (size_t)2 * h->hm.prog_off[3] * 3));
+    if (value && !h->prof) CK(dalloc(&h->prof, (size_t)2 * h->hm.prog_off[3] * 8));
     h->hm.prof = value ? h->prof : nullptr;
     CK(cudaMemcpy(h->dm, &h->hm, sizeof(DecModel), cudaMemcpyHostToDevice));
     return WM_OK;
@@ -729,25 +737,28 @@ extern "C" int wm_set_option(wm_handle* h, const char* key, int32_t value) {
   return fail(h, WM_ERR_INVALID, "unknown option " + k);
 }
 // Stage timeline of the last persistent-ring iteration (option "profile" = 1): rows of
-// {stage, mode, layer, body_ns(cta 0), barrier_ns(cta 0), body_ns(last cta), barrier_ns(last cta)}
+// {stage, mode, layer, body_ns(cta 0), barrier_ns(cta 0), body_ns(last cta), barrier_ns(last cta),
+//  4 GEMM sub-phase offsets (ns since stage begin, CTA 0)}  -- 11 int64 per row
 extern "C" int wm_get_stage_profile(wm_handle* h, int64_t* out, int32_t cap_rows, int32_t* n_rows) {
   if (!h || !out || !n_rows) return WM_ERR_INVALID;
   if (!h->prof) return fail(h, WM_ERR_STATE, "profiling is off (wm_set_option(h, \"profile\", 1))");
   CK(cudaSetDevice(h->device));
   const int n = h->hm.prog_off[3];
-  std::vector<unsigned long long> raw((size_t)2 * n * 3);
+  std::vector<unsigned long long> raw((size_t)2 * n * 8);
   std::vector<int> prog((size_t)n * 3);
   CK(cudaMemcpy(raw.data(), h->prof, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(prog.data(), h->prog, prog.size() * sizeof(int), cudaMemcpyDeviceToHost));
   int rows = 0;
   for (int i = 0; i < n && rows < cap_rows; ++i) {
-    const unsigned long long* a = &raw[(size_t)i * 3];
-    const unsigned long long* b = &raw[((size_t)n + i) * 3];
+    const unsigned long long* a = &raw[(size_t)i * 8];
+    const unsigned long long* b = &raw[((size_t)n + i) * 8];
     if (a[0] == 0) continue;   // stage not executed in the last iteration (sweep A skipped)
-    int64_t* o = out + (size_t)rows * 7;
+    int64_t* o = out + (size_t)rows * 11;
     o[0] = prog[i * 3]; o[1] = prog[i * 3 + 1]; o[2] = prog[i * 3 + 2];
     o[3] = (int64_t)(a[1] - a[0]); o[4] = (int64_t)(a[2] - a[1]);
     o[5] = (int64_t)(b[1] - b[0]); o[6] = (int64_t)(b[2] - b[1]);
+    // GEMM stages (CTA 0): X staged, first chunk ready, first chunk MMAs done, first chunk epilogue done
+    for (int k = 0; k < 4; ++k) o[7 + k] = a[3 + k] >= a[0] ? (int64_t)(a[3 + k] - a[0]) : -1;
     ++rows;
   }
   *n_rows = rows;
