@@ -157,6 +157,7 @@ struct DecModel {
   float* head_h;   // [WM_MAX_T, d]
   float* carry;    // [d] final-LN hidden state of the newest cached token (input of the heads)
   float* cross_part;  // [H][WM_CROSS_CHUNKS][WM_MAX_T][WM_HEAD_DIM + 2]
+  int cross_chunks;   // key chunks per head of the cross-attention stage: clamp(n_sm / H, 1, 8)
   unsigned int* cross_cnt;  // [H] arrival counters of the cross-attention chunks (last arriver combines)
   float* gemm_part;   // [8 k-segments][WM_MAX_T][d] partial sums of K-split GEMM stages (FC2)
   unsigned int* gemm_cnt;  // [n_sm] arrival counters of their row blocks (last arriver folds)

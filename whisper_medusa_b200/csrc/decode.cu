@@ -51,7 +51,7 @@ __device__ __forceinline__ PassGeom pass_geom(const DecModel* m, int mode) {
 // -----------------------------------------------------------------------------------------
 // stage: token + position embedding  (HF modeling_whisper.py:737-763)
 // -----------------------------------------------------------------------------------------
-__device__ void stage_embed(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
+__device__ __noinline__ void stage_embed(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
   const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const DecState* st = m->st;
   const int d = m->d;
@@ -149,7 +149,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmDesc& g, int token, int 
   }
 }
 
-__device__ void stage_gemm(const GemmDesc& g, int cta, int ncta, unsigned char* smem_raw) {
+__device__ __noinline__ void stage_gemm(const GemmDesc& g, int cta, int ncta, unsigned char* smem_raw) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = (WM_DEC_THREADS >> 5);
   const int gq = lane >> 2, tq = lane & 3;
@@ -311,199 +311,239 @@ __device__ void stage_gemm(const GemmDesc& g, int cta, int ncta, unsigned char* 
 
 // -----------------------------------------------------------------------------------------
 // stage: causal self-attention over the fp16 cache (HF modeling_whisper.py:284-357, T_q <= 16)
-// item = (head, query row); keys 0 .. base + t
+// item = (head, group of R query rows); R = ceil(H*T / n_cta) so that all items run in ONE wave.
+// Row t sees keys 0 .. base + t.  K/V rows come straight from L2 (the cache is small and hot).
 // -----------------------------------------------------------------------------------------
-__device__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
-  const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
-  const int d = m->d, H = m->H;
-  const DecLayer& L = m->layers[layer];
-  float* s_q = reinterpret_cast<float*>(smem_raw);            // [64]
-  float* s_p = s_q + 64;                                      // [WM_MAX_POS]
-  float* s_red = s_p + WM_MAX_POS;                            // [64]
-  float* s_acc = s_red + 64;                                  // [64 groups][64]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (WM_DEC_THREADS >> 5);
-  for (int item = cta; item < H * g.T; item += ncta) {
-    const int h = item / g.T, t = item - h * g.T;
-    const int nk = g.base + t + 1;
-    cta_sync();
-    if (tid < 64) s_q[tid] = m->q[(size_t)t * d + h * 64 + tid];
-    cta_sync();
-    // scores
-    float lmax = -INFINITY;
-    for (int j = tid; j < nk; j += WM_DEC_THREADS) {
-      const uint4* kp = reinterpret_cast<const uint4*>(L.self_k + (size_t)j * d + h * 64);
-      float s = 0.f;
+#define WM_SA_MAXR 4
+__host__ __device__ inline size_t self_attn_smem_bytes() {
+  return (size_t)(WM_SA_MAXR * 64 + WM_SA_MAXR * WM_MAX_POS + 2 * WM_SA_MAXR + 60 * 64) * sizeof(float);
+}
+__device__ __forceinline__ float dot64_h(const float* q, const uint4* kp) {
+  float s = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 kv = kp[c];
-        const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+  for (int c = 0; c < 8; ++c) {
+    const uint4 kv = kp[c];
+    const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2 f = __half22float2(k2[e]);
-          s = fmaf(s_q[c * 8 + 2 * e], f.x, s);
-          s = fmaf(s_q[c * 8 + 2 * e + 1], f.y, s);
-        }
-      }
-      s *= 0.125f;  // head_dim^-0.5 (HF scales q; a power of two, so scaling the score is identical)
-      s_p[j] = s;
-      lmax = fmaxf(lmax, s);
-    }
-    lmax = warp_max(lmax);
-    if (lane == 0) s_red[warp] = lmax;
-    cta_sync();
-    float gmax = -INFINITY;
-    for (int w = 0; w < nwarps; ++w) gmax = fmaxf(gmax, s_red[w]);
-    cta_sync();
-    float lsum = 0.f;
-    for (int j = tid; j < nk; j += WM_DEC_THREADS) {
-      float p = expf(s_p[j] - gmax);
-      s_p[j] = p;
-      lsum += p;
-    }
-    lsum = warp_sum(lsum);
-    if (lane == 0) s_red[32 + warp] = lsum;
-    cta_sync();
-    float gsum = 0.f;
-    for (int w = 0; w < nwarps; ++w) gsum += s_red[32 + w];
-    // P * V : thread = (key group kg, dim group dg of 8 dims)
-    const int dg = tid & 7, kg = tid >> 3, ngroups = (WM_DEC_THREADS >> 3);
-    float a[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) a[e] = 0.f;
-    for (int j = kg; j < nk; j += ngroups) {
-      uint4 vv = *reinterpret_cast<const uint4*>(L.self_v + (size_t)j * d + h * 64 + dg * 8);
-      const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
-      const float p = s_p[j];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __half22float2(v2[e]);
-        a[2 * e] = fmaf(p, f.x, a[2 * e]);
-        a[2 * e + 1] = fmaf(p, f.y, a[2 * e + 1]);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) s_acc[kg * 64 + dg * 8 + e] = a[e];
-    cta_sync();
-    if (tid < 64) {
-      float o = 0.f;
-      for (int gI = 0; gI < ngroups; ++gI) o += s_acc[gI * 64 + tid];
-      m->attn[(size_t)t * d + h * 64 + tid] = o / gsum;
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(k2[e]);
+      s = fmaf(q[c * 8 + 2 * e], f.x, s);
+      s = fmaf(q[c * 8 + 2 * e + 1], f.y, s);
     }
   }
+  return s;
 }
-__host__ __device__ inline size_t self_attn_smem_bytes() {
-  return (size_t)(64 + WM_MAX_POS + 64 + 64 * 64) * sizeof(float);
-}
-
-// -----------------------------------------------------------------------------------------
-// stage: cross-attention partials over one key chunk (flash-decoding split over WM_CROSS_CHUNKS)
-// item = (head, chunk); all T query rows at once.  K/V rows: cross_kv[pos][0:d | d:2d].
-// -----------------------------------------------------------------------------------------
-#define WM_CH_MAX 192
-__host__ __device__ inline size_t cross_attn_smem_bytes() {
-  return (size_t)WM_CH_MAX * 72 * sizeof(__half) + (size_t)WM_CH_MAX * 64 * sizeof(__half) +
-         (size_t)WM_MAX_T * WM_CH_MAX * sizeof(float) + (size_t)WM_MAX_T * 64 * sizeof(float) +
-         (size_t)2 * WM_MAX_T * sizeof(float);
-}
-__device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
+__device__ __noinline__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
   const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
-  const int d = m->d, H = m->H, S = m->S;
+  const int d = m->d, H = m->H, T = g.T;
   const DecLayer& L = m->layers[layer];
-  const int CH = (S + WM_CROSS_CHUNKS - 1) / WM_CROSS_CHUNKS;
-  __half* sK = reinterpret_cast<__half*>(smem_raw);                 // [CH][72]
-  __half* sV = sK + WM_CH_MAX * 72;                                 // [CH][64]
-  float* sS = reinterpret_cast<float*>(sV + WM_CH_MAX * 64);        // [16][WM_CH_MAX]
-  float* sQ = sS + WM_MAX_T * WM_CH_MAX;                            // [16][64]
-  float* sM = sQ + WM_MAX_T * 64;                                   // [16] max, [16] sum
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (WM_DEC_THREADS >> 5);
-  const int T = g.T;
-  __shared__ int s_last;
-  for (int item = cta; item < H * WM_CROSS_CHUNKS; item += ncta) {
-    const int h = item / WM_CROSS_CHUNKS, c = item - h * WM_CROSS_CHUNKS;
-    const int j0 = c * CH, nk = max(0, min(S, j0 + CH) - j0);
+  float* s_q = reinterpret_cast<float*>(smem_raw);                 // [R][64]
+  float* s_p = s_q + WM_SA_MAXR * 64;                              // [R][WM_MAX_POS]
+  float* s_st = s_p + WM_SA_MAXR * WM_MAX_POS;                     // [R] sum
+  float* s_acc = s_st + 2 * WM_SA_MAXR;                            // [60 groups][64]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int R = (H * T + ncta - 1) / ncta;
+  if (R > WM_SA_MAXR) R = WM_SA_MAXR;
+  if (R < 1) R = 1;
+  const int groups = (T + R - 1) / R;
+  for (int item = cta; item < H * groups; item += ncta) {
+    const int h = item / groups, t0 = (item - h * groups) * R;
+    const int rg = min(R, T - t0);                 // rows in this group
+    const int nk_max = g.base + t0 + rg;           // keys of the last row of the group
     cta_sync();
-    for (int idx = tid; idx < nk * 8; idx += WM_DEC_THREADS) {
-      int j = idx >> 3, part = idx & 7;
-      const __half* src = L.cross_kv + (size_t)(j0 + j) * 2 * d + h * 64 + part * 8;
-      *reinterpret_cast<uint4*>(sK + j * 72 + part * 8) = ldg_nc_v4(src);
-      *reinterpret_cast<uint4*>(sV + j * 64 + part * 8) = ldg_nc_v4(src + d);
-    }
-    for (int idx = tid; idx < T * 64; idx += WM_DEC_THREADS) {
-      int t = idx >> 6, e = idx & 63;
-      sQ[idx] = m->q[(size_t)t * d + h * 64 + e];
-    }
+    for (int idx = tid; idx < rg * 64; idx += WM_DEC_THREADS)
+      s_q[idx] = m->q[(size_t)(t0 + (idx >> 6)) * d + h * 64 + (idx & 63)];
     cta_sync();
-    // scores for all (t, j)
-    for (int idx = tid; idx < T * nk; idx += WM_DEC_THREADS) {
-      int t = idx / nk, j = idx - t * nk;
-      const float* q = sQ + t * 64;
-      const uint4* kp = reinterpret_cast<const uint4*>(sK + j * 72);
-      float s = 0.f;
+    // scores (scaled by head_dim^-0.5; HF scales q, a power of two, so this is identical)
+    const int npairs = rg * nk_max;
+    for (int i0 = tid; i0 < npairs; i0 += 2 * WM_DEC_THREADS) {
+      const int i1 = i0 + WM_DEC_THREADS;
+      const int r0 = i0 / nk_max, j0 = i0 - r0 * nk_max;
+      const bool has1 = i1 < npairs;
+      const int r1 = has1 ? i1 / nk_max : 0, j1 = has1 ? i1 - r1 * nk_max : 0;
+      const uint4* k0 = reinterpret_cast<const uint4*>(L.self_k + (size_t)j0 * d + h * 64);
+      const uint4* k1 = reinterpret_cast<const uint4*>(L.self_k + (size_t)j1 * d + h * 64);
+      uint4 a[8], b[8];
 #pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        uint4 kv = kp[cc];
-        const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2 f = __half22float2(k2[e]);
-          s = fmaf(q[cc * 8 + 2 * e], f.x, s);
-          s = fmaf(q[cc * 8 + 2 * e + 1], f.y, s);
-        }
-      }
-      sS[t * WM_CH_MAX + j] = s * 0.125f;  // head_dim^-0.5
+      for (int c = 0; c < 8; ++c) { a[c] = k0[c]; b[c] = k1[c]; }
+      const bool ok0 = j0 <= g.base + t0 + r0;     // causal
+      const bool ok1 = has1 && (j1 <= g.base + t0 + r1);
+      s_p[r0 * WM_MAX_POS + j0] = ok0 ? dot64_h(s_q + r0 * 64, a) * 0.125f : -INFINITY;
+      if (has1) s_p[r1 * WM_MAX_POS + j1] = ok1 ? dot64_h(s_q + r1 * 64, b) * 0.125f : -INFINITY;
     }
     cta_sync();
-    // per-row max / exp / sum : warp per row
-    for (int t = warp; t < T; t += nwarps) {
+    // softmax statistics: one warp per row
+    for (int r = warp; r < rg; r += (WM_DEC_THREADS >> 5)) {
+      const int nk = g.base + t0 + r + 1;
+      float* p = s_p + r * WM_MAX_POS;
       float mx = -INFINITY;
-      for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, sS[t * WM_CH_MAX + j]);
+      for (int jj = lane; jj < nk; jj += 32) mx = fmaxf(mx, p[jj]);
       mx = warp_max(mx);
       float sum = 0.f;
-      for (int j = lane; j < nk; j += 32) {
-        float p = expf(sS[t * WM_CH_MAX + j] - mx);
-        sS[t * WM_CH_MAX + j] = p;
-        sum += p;
-      }
+      for (int jj = lane; jj < nk; jj += 32) { const float e = expf(p[jj] - mx); p[jj] = e; sum += e; }
       sum = warp_sum(sum);
-      if (lane == 0) { sM[t] = mx; sM[WM_MAX_T + t] = sum; }
+      if (lane == 0) s_st[r] = sum;
     }
     cta_sync();
-    // P * V : warp per row t; lane = (kg of 4, dg of 8)
-    for (int t = warp; t < T; t += nwarps) {
-      const int dg = lane & 7, kg = lane >> 3;
+    // P * V : thread = (row r, key group kg, dim group dg of 8 dims)
+    {
+      const int KG = 60 / rg;
+      const int dg = tid & 7, gI = tid >> 3;       // 60 groups of 8 threads
+      const int r = gI / KG, kg = gI - r * KG;
       float a[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) a[e] = 0.f;
-      for (int j = kg; j < nk; j += 4) {
-        uint4 vv = *reinterpret_cast<const uint4*>(sV + j * 64 + dg * 8);
-        const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
-        const float p = sS[t * WM_CH_MAX + j];
+      if (r < rg) {
+        const int nk = g.base + t0 + r + 1;
+        const float* p = s_p + r * WM_MAX_POS;
+#pragma unroll 4
+        for (int jj = kg; jj < nk; jj += KG) {
+          const uint4 vv = *reinterpret_cast<const uint4*>(L.self_v + (size_t)jj * d + h * 64 + dg * 8);
+          const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+          const float pj = p[jj];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2 f = __half22float2(v2[e]);
-          a[2 * e] = fmaf(p, f.x, a[2 * e]);
-          a[2 * e + 1] = fmaf(p, f.y, a[2 * e + 1]);
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(v2[e]);
+            a[2 * e] = fmaf(pj, f.x, a[2 * e]);
+            a[2 * e + 1] = fmaf(pj, f.y, a[2 * e + 1]);
+          }
         }
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 8);
-        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 16);
+      for (int e = 0; e < 8; ++e) s_acc[gI * 64 + dg * 8 + e] = a[e];
+      cta_sync();
+      if (tid < rg * 64) {
+        const int rr = tid >> 6, c = tid & 63;
+        float o = 0.f;
+        for (int k2 = 0; k2 < KG; ++k2) o += s_acc[(rr * KG + k2) * 64 + c];
+        m->attn[(size_t)(t0 + rr) * d + h * 64 + c] = o / s_st[rr];
       }
-      float* out = m->cross_part + ((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + t) * (WM_HEAD_DIM + 2);
-      if (kg == 0) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) out[dg * 8 + e] = a[e];
-      }
-      if (lane == 0) { out[64] = sM[t]; out[65] = sM[WM_MAX_T + t]; }
     }
-    // The chunk that arrives last for this head folds the WM_CROSS_CHUNKS partials (always in chunk
-    // order => deterministic) -- no separate combine stage / grid barrier.
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// stage: cross-attention over the encoder K/V (flash-decoding split: m->cross_chunks key chunks per head)
+// item = (head, chunk); all T query rows at once.  K/V rows: cross_kv[pos][0:d | d:2d] fp16.
+// The chunk that arrives last for a head folds the partials (chunk order => deterministic).
+// -----------------------------------------------------------------------------------------
+#define WM_CH_MAX 216
+__host__ __device__ inline size_t cross_attn_smem_bytes() {
+  return (size_t)WM_CH_MAX * 72 * sizeof(__half) + (size_t)WM_CH_MAX * 64 * sizeof(__half) +
+         (size_t)WM_MAX_T * WM_CH_MAX * sizeof(float) + (size_t)2 * WM_MAX_T * sizeof(float);
+}
+__device__ __noinline__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
+  const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
+  const int d = m->d, H = m->H, S = m->S;
+  const DecLayer& L = m->layers[layer];
+  const int nch = m->cross_chunks;
+  const int CH = (S + nch - 1) / nch;
+  __half* sK = reinterpret_cast<__half*>(smem_raw);                 // [CH][72]   (reused as sAcc after the scores)
+  __half* sV = sK + WM_CH_MAX * 72;                                 // [CH][64]
+  float* sS = reinterpret_cast<float*>(sV + WM_CH_MAX * 64);        // [16][WM_CH_MAX]
+  float* sM = sS + WM_MAX_T * WM_CH_MAX;                            // [16] max, [16] sum
+  float* sAcc = reinterpret_cast<float*>(sK);                       // [KS][T][64] floats  (<= 16 KB < sizeof sK)
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (WM_DEC_THREADS >> 5);
+  const int T = g.T;
+  for (int item = cta; item < H * nch; item += ncta) {
+    const int h = item / nch, c = item - h * nch;
+    const int j0 = c * CH, nk = max(0, min(S, j0 + CH) - j0);
+    cta_sync();
+    // K / V chunk -> shared memory (all loads of a batch in flight before the first store)
+    for (int base = 0; base < nk * 8; base += 4 * WM_DEC_THREADS) {
+      uint4 kk[4], vv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = base + i * WM_DEC_THREADS + tid;
+        if (idx < nk * 8) {
+          const __half* src = L.cross_kv + (size_t)(j0 + (idx >> 3)) * 2 * d + h * 64 + (idx & 7) * 8;
+          kk[i] = ldg_nc_v4(src);
+          vv[i] = ldg_nc_v4(src + d);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = base + i * WM_DEC_THREADS + tid;
+        if (idx < nk * 8) {
+          *reinterpret_cast<uint4*>(sK + (idx >> 3) * 72 + (idx & 7) * 8) = kk[i];
+          *reinterpret_cast<uint4*>(sV + (idx >> 3) * 64 + (idx & 7) * 8) = vv[i];
+        }
+      }
+    }
+    // scores: P threads per query row, the query in registers, keys strided over the P threads
+    const int P = WM_DEC_THREADS / T;
+    const int t = tid / P, pI = tid - t * P;
+    float q[64];
+    if (t < T) {
+      const float4* q4 = reinterpret_cast<const float4*>(m->q + (size_t)t * d + h * 64);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { const float4 v = q4[i]; q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w; }
+    }
+    cta_sync();
+    if (t < T) {
+      for (int jj = pI; jj < nk; jj += P)
+        sS[t * WM_CH_MAX + jj] = dot64_h(q, reinterpret_cast<const uint4*>(sK + jj * 72)) * 0.125f;   // head_dim^-0.5
+    }
+    cta_sync();
+    // per-row max / exp / sum : warp per row
+    for (int r = warp; r < T; r += nwarps) {
+      float mx = -INFINITY;
+      for (int jj = lane; jj < nk; jj += 32) mx = fmaxf(mx, sS[r * WM_CH_MAX + jj]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int jj = lane; jj < nk; jj += 32) {
+        const float p = expf(sS[r * WM_CH_MAX + jj] - mx);
+        sS[r * WM_CH_MAX + jj] = p;
+        sum += p;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) { sM[r] = mx; sM[WM_MAX_T + r] = sum; }
+    }
+    cta_sync();
+    // P * V : thread = (key slice ks, row r, dim group dg); partial sums per key slice in shared memory
+    {
+      int KS = WM_DEC_THREADS / (T * 8);
+      if (KS > 60) KS = 60;
+      const int ks = tid / (T * 8), rem = tid - ks * (T * 8);
+      const int r = rem >> 3, dg = rem & 7;
+      float a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = 0.f;
+      if (ks < KS) {
+        for (int jj = ks; jj < nk; jj += KS) {
+          const uint4 vv = *reinterpret_cast<const uint4*>(sV + jj * 64 + dg * 8);
+          const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+          const float p = sS[r * WM_CH_MAX + jj];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(v2[e]);
+            a[2 * e] = fmaf(p, f.x, a[2 * e]);
+            a[2 * e + 1] = fmaf(p, f.y, a[2 * e + 1]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sAcc[((size_t)ks * T + r) * 64 + dg * 8 + e] = a[e];   // sK is dead by now
+      }
+      cta_sync();
+      for (int idx = tid; idx < T * 64; idx += WM_DEC_THREADS) {
+        const int rr = idx >> 6, cc = idx & 63;
+        float o = 0.f;
+        for (int k2 = 0; k2 < KS; ++k2) o += sAcc[((size_t)k2 * T + rr) * 64 + cc];
+        m->cross_part[((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + rr) * (WM_HEAD_DIM + 2) + cc] = o;
+      }
+      if (tid < T) {
+        float* out = m->cross_part + ((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + tid) * (WM_HEAD_DIM + 2);
+        out[64] = sM[tid];
+        out[65] = sM[WM_MAX_T + tid];
+      }
+    }
+    // fold: the chunk that arrives last for this head (always in chunk order => deterministic)
     __threadfence();
     cta_sync();
     if (tid == 0) {
       const unsigned int prev = atomicAdd(&m->cross_cnt[h], 1u);
-      s_last = (prev == WM_CROSS_CHUNKS - 1) ? 1 : 0;
+      s_last = (prev == (unsigned int)(nch - 1)) ? 1 : 0;
       if (s_last) m->cross_cnt[h] = 0u;   // everybody has arrived: re-arm for the next layer
     }
     cta_sync();
@@ -511,19 +551,17 @@ __device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta
       __threadfence();
       const size_t cstride = (size_t)WM_MAX_T * (WM_HEAD_DIM + 2);
       for (int idx = tid; idx < T * 64; idx += WM_DEC_THREADS) {
-        const int t = idx >> 6, e = idx & 63;
-        const float* base = m->cross_part + ((size_t)h * WM_CROSS_CHUNKS * WM_MAX_T + t) * (WM_HEAD_DIM + 2);
+        const int rr = idx >> 6, e = idx & 63;
+        const float* base = m->cross_part + ((size_t)h * WM_CROSS_CHUNKS * WM_MAX_T + rr) * (WM_HEAD_DIM + 2);
         float M = -INFINITY;
-#pragma unroll
-        for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc) M = fmaxf(M, __ldcg(base + cc * cstride + 64));
+        for (int cc = 0; cc < nch; ++cc) M = fmaxf(M, __ldcg(base + cc * cstride + 64));
         float num = 0.f, den = 0.f;
-#pragma unroll
-        for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc) {
+        for (int cc = 0; cc < nch; ++cc) {
           const float w = expf(__ldcg(base + cc * cstride + 64) - M);
           num = fmaf(w, __ldcg(base + cc * cstride + e), num);
           den = fmaf(w, __ldcg(base + cc * cstride + 65), den);
         }
-        m->attn[(size_t)t * d + h * 64 + e] = num / den;
+        m->attn[(size_t)rr * d + h * 64 + e] = num / den;
       }
     }
   }
@@ -535,7 +573,7 @@ __device__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta
 //            input of the Medusa heads).  sweep B + block type: base logits read the hidden
 //            states directly (reference model.py:1287).
 // -----------------------------------------------------------------------------------------
-__device__ void stage_final_ln(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
+__device__ __noinline__ void stage_final_ln(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
   const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const int d = m->d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -648,7 +686,7 @@ __device__ float block_sum(float v, float* s_val) {
 __device__ __forceinline__ int select_nseg(const DecModel* m, int /*ncta*/) { return m->sel_nseg; }
 // sel_part layout: [row][seg][4] = {max, argmax (int bits), sumexp, entropy term}
 
-__device__ void stage_select1(const DecModel* m, int mode, int cta, int ncta, unsigned char* smem_raw) {
+__device__ __noinline__ void stage_select1(const DecModel* m, int mode, int cta, int ncta, unsigned char* smem_raw) {
   const DecState* st = m->st;
   const int V = m->V, K = m->K;
   float* s_val = reinterpret_cast<float*>(smem_raw);
@@ -702,7 +740,7 @@ __device__ __forceinline__ void select_fold(const DecModel* m, int r, int nseg, 
   }
 }
 
-__device__ void stage_select2(const DecModel* m, int cta, int ncta, unsigned char* smem_raw) {
+__device__ __noinline__ void stage_select2(const DecModel* m, int cta, int ncta, unsigned char* smem_raw) {
   DecState* st = m->st;
   const int V = m->V, K = m->K;
   float* s_val = reinterpret_cast<float*>(smem_raw);
@@ -761,7 +799,7 @@ __device__ void stage_select_fin(const DecModel* m, int ncta) {
 //   accept-0 iteration (second emitted token = argmax of the verify row, never seen by the
 //   decoder) a one-token sweep A is needed (`need_a`).
 // -----------------------------------------------------------------------------------------
-__device__ void stage_accept(const DecModel* m, int ncta) {
+__device__ __noinline__ void stage_accept(const DecModel* m, int ncta) {
   __shared__ int s_a;
   DecState* st = m->st;
   const int K = m->K;
@@ -1079,7 +1117,7 @@ static int stage_grid(int stage, int T, int n_sm, int H, int K) {
   switch (stage) {
     case ST_EMBED: return T;
     case ST_SELF_ATTN: return H * T;
-    case ST_CROSS_ATTN: return H * WM_CROSS_CHUNKS;
+    case ST_CROSS_ATTN: return H * WM_CROSS_CHUNKS;   // upper bound; items = H * m->cross_chunks
     case ST_FINAL_LN: return 1;
     case ST_COPY_HIDDEN: return 8;
     case ST_TAIL_SEED: return 2;

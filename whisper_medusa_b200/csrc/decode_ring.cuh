@@ -134,7 +134,7 @@ struct RingCtx {
 // ---------------------------------------------------------------------------------------------
 // producer warp: stream the chunk table through the ring
 // ---------------------------------------------------------------------------------------------
-__device__ void ring_producer(const RingCtx& rc, const ChunkDesc* __restrict__ tab, int first, int last) {
+__device__ __noinline__ void ring_producer(const RingCtx& rc, const ChunkDesc* __restrict__ tab, int first, int last) {
   const int lane = threadIdx.x & 31;
   if (first >= last) return;
   ChunkDesc nxt = tab[first];
@@ -176,7 +176,7 @@ __device__ __forceinline__ void store_hilo4(__half* hi, __half* lo, float4 y) {
 
 #define WM_LN_MAXV 10   // float4 per lane: d <= 1280 (every Whisper size)
 
-__device__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __half* xlo, int xstride, int& rows_dirty) {
+__device__ __noinline__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __half* xlo, int xstride, int& rows_dirty) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = WM_DEC_THREADS >> 5;
   const int T = g.x_rows;
   if (g.xsrc == XS_LN) {
@@ -257,7 +257,7 @@ __device__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __h
 // ---------------------------------------------------------------------------------------------
 // GEMM stage fed from the ring (compute warps)
 // ---------------------------------------------------------------------------------------------
-__device__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, const GemmDesc& g, __half* xhi, __half* xlo, float* partial,
+__device__ __noinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, const GemmDesc& g, __half* xhi, __half* xlo, float* partial,
                                 int& rows_dirty, unsigned long long* pr) {
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -269,6 +269,9 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   CK(dalloc(&m.carry, d));
   CK(dalloc(&m.cross_part, (size_t)c.n_heads * WM_CROSS_CHUNKS * WM_MAX_T * (WM_HEAD_DIM + 2)));
   CK(dalloc(&m.cross_cnt, (size_t)c.n_heads));
+  m.cross_chunks = h->n_sm / c.n_heads;
+  if (m.cross_chunks < 1) m.cross_chunks = 1;
+  if (m.cross_chunks > WM_CROSS_CHUNKS) m.cross_chunks = WM_CROSS_CHUNKS;
   if (f % d != 0 || f / d > 8 || h->n_sm < (int)(f / d)) return fail(h, WM_ERR_UNSUPPORTED, "ffn_dim must be a multiple (<= 8x) of d_model");
   CK(dalloc(&m.gemm_part, (size_t)8 * WM_MAX_T * d));
   CK(dalloc(&m.gemm_cnt, (size_t)h->n_sm));
