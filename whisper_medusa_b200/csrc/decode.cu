@@ -149,6 +149,21 @@ __device__ __forceinline__ void gemm_epilogue(const GemmDesc& g, int token, int 
   }
 }
 
+// Medusa-head epilogues of the ring kernel (rare: twice per iteration).  Out of line and with scalar
+// arguments only, so that the GemmDesc of the caller never has to live in local memory.
+__device__ __noinline__ void gemm_epilogue_heads(int epi, float* out, int ldo, int out_row0, int dm, float bias, int token,
+                                                 int row, float v, const __half* xhi, const __half* xlo, int xstride) {
+  v += bias;
+  if (epi == EPI_HEADS_A) {
+    const int head = row / dm, n = row - head * dm;
+    const float xv = __half2float(xhi[n]) + __half2float(xlo[n]);
+    out[(size_t)(out_row0 + head) * ldo + n] = xv + silu(v);
+  } else {
+    const float xv = __half2float(xhi[(size_t)token * xstride + row]) + __half2float(xlo[(size_t)token * xstride + row]);
+    out[(size_t)token * ldo + row] = xv + silu(v);
+  }
+}
+
 __device__ __noinline__ void stage_gemm(const GemmDesc& g, int cta, int ncta, unsigned char* smem_raw) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = (WM_DEC_THREADS >> 5);
@@ -333,7 +348,7 @@ __device__ __forceinline__ float dot64_h(const float* q, const uint4* kp) {
   }
   return s;
 }
-__device__ __noinline__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
+__device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
   const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const int d = m->d, H = m->H, T = g.T;
   const DecLayer& L = m->layers[layer];
@@ -356,20 +371,14 @@ __device__ __noinline__ void stage_self_attn(const DecModel* m, int mode, int la
     cta_sync();
     // scores (scaled by head_dim^-0.5; HF scales q, a power of two, so this is identical)
     const int npairs = rg * nk_max;
-    for (int i0 = tid; i0 < npairs; i0 += 2 * WM_DEC_THREADS) {
-      const int i1 = i0 + WM_DEC_THREADS;
+    for (int i0 = tid; i0 < npairs; i0 += WM_DEC_THREADS) {
       const int r0 = i0 / nk_max, j0 = i0 - r0 * nk_max;
-      const bool has1 = i1 < npairs;
-      const int r1 = has1 ? i1 / nk_max : 0, j1 = has1 ? i1 - r1 * nk_max : 0;
       const uint4* k0 = reinterpret_cast<const uint4*>(L.self_k + (size_t)j0 * d + h * 64);
-      const uint4* k1 = reinterpret_cast<const uint4*>(L.self_k + (size_t)j1 * d + h * 64);
-      uint4 a[8], b[8];
+      uint4 a[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) { a[c] = k0[c]; b[c] = k1[c]; }
+      for (int c = 0; c < 8; ++c) a[c] = k0[c];
       const bool ok0 = j0 <= g.base + t0 + r0;     // causal
-      const bool ok1 = has1 && (j1 <= g.base + t0 + r1);
       s_p[r0 * WM_MAX_POS + j0] = ok0 ? dot64_h(s_q + r0 * 64, a) * 0.125f : -INFINITY;
-      if (has1) s_p[r1 * WM_MAX_POS + j1] = ok1 ? dot64_h(s_q + r1 * 64, b) * 0.125f : -INFINITY;
     }
     cta_sync();
     // softmax statistics: one warp per row
@@ -427,28 +436,41 @@ __device__ __noinline__ void stage_self_attn(const DecModel* m, int mode, int la
 // item = (head, chunk); all T query rows at once.  K/V rows: cross_kv[pos][0:d | d:2d] fp16.
 // The chunk that arrives last for a head folds the partials (chunk order => deterministic).
 // -----------------------------------------------------------------------------------------
-#define WM_CH_MAX 216
+#define WM_CH_MAX 216   // keys per chunk (S = 1500 over >= 7 chunks)
+#define WM_CH_PAD 224   // rounded up to the MMA k-step (16 keys)
 __host__ __device__ inline size_t cross_attn_smem_bytes() {
-  return (size_t)WM_CH_MAX * 72 * sizeof(__half) + (size_t)WM_CH_MAX * 64 * sizeof(__half) +
-         (size_t)WM_MAX_T * WM_CH_MAX * sizeof(float) + (size_t)2 * WM_MAX_T * sizeof(float);
+  return (size_t)2 * WM_CH_PAD * 72 * sizeof(__half) + (size_t)WM_MAX_T * WM_CH_PAD * sizeof(float) +
+         (size_t)2 * 16 * 72 * sizeof(__half) + (size_t)2 * WM_MAX_T * sizeof(float);
 }
-__device__ __noinline__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
+__device__ __forceinline__ void split_hilo(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+  __half2 h = __halves2half2(ha, hb);
+  __half2 l = __floats2half2_rn(a - __half2float(ha), b - __half2float(hb));
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+// Both products run on the tensor cores (mma.sync m16n8k16, fp32 accumulate): S = Q K^T with the
+// fp32 query split into fp16 hi + lo, O = P V with the fp32 probabilities split the same way.
+__device__ __forceinline__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
   const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const int d = m->d, H = m->H, S = m->S;
   const DecLayer& L = m->layers[layer];
   const int nch = m->cross_chunks;
   const int CH = (S + nch - 1) / nch;
-  __half* sK = reinterpret_cast<__half*>(smem_raw);                 // [CH][72]   (reused as sAcc after the scores)
-  __half* sV = sK + WM_CH_MAX * 72;                                 // [CH][64]
-  float* sS = reinterpret_cast<float*>(sV + WM_CH_MAX * 64);        // [16][WM_CH_MAX]
-  float* sM = sS + WM_MAX_T * WM_CH_MAX;                            // [16] max, [16] sum
-  float* sAcc = reinterpret_cast<float*>(sK);                       // [KS][T][64] floats  (<= 16 KB < sizeof sK)
+  __half* sK = reinterpret_cast<__half*>(smem_raw);                 // [CH_PAD][72]
+  __half* sV = sK + WM_CH_PAD * 72;                                 // [CH_PAD][72]
+  float* sS = reinterpret_cast<float*>(sV + WM_CH_PAD * 72);        // [16][CH_PAD]  scores, then probabilities
+  __half* sQh = reinterpret_cast<__half*>(sS + WM_MAX_T * WM_CH_PAD);   // [16][72]
+  __half* sQl = sQh + 16 * 72;
+  float* sM = reinterpret_cast<float*>(sQl + 16 * 72);              // [16] max, [16] sum
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (WM_DEC_THREADS >> 5);
+  const int gq = lane >> 2, tq = lane & 3;
   const int T = g.T;
   for (int item = cta; item < H * nch; item += ncta) {
     const int h = item / nch, c = item - h * nch;
     const int j0 = c * CH, nk = max(0, min(S, j0 + CH) - j0);
+    const int nk_pad = (nk + 15) & ~15;
     cta_sync();
     // K / V chunk -> shared memory (all loads of a batch in flight before the first store)
     for (int base = 0; base < nk * 8; base += 4 * WM_DEC_THREADS) {
@@ -467,76 +489,100 @@ __device__ __noinline__ void stage_cross_attn(const DecModel* m, int mode, int l
         const int idx = base + i * WM_DEC_THREADS + tid;
         if (idx < nk * 8) {
           *reinterpret_cast<uint4*>(sK + (idx >> 3) * 72 + (idx & 7) * 8) = kk[i];
-          *reinterpret_cast<uint4*>(sV + (idx >> 3) * 64 + (idx & 7) * 8) = vv[i];
+          *reinterpret_cast<uint4*>(sV + (idx >> 3) * 72 + (idx & 7) * 8) = vv[i];
         }
       }
     }
-    // scores: P threads per query row, the query in registers, keys strided over the P threads
-    const int P = WM_DEC_THREADS / T;
-    const int t = tid / P, pI = tid - t * P;
-    float q[64];
-    if (t < T) {
-      const float4* q4 = reinterpret_cast<const float4*>(m->q + (size_t)t * d + h * 64);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { const float4 v = q4[i]; q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w; }
+    // rows nk .. nk_pad of K and V read as zero (their probabilities are zero, but 0 * garbage could be NaN)
+    for (int idx = tid; idx < (nk_pad - nk) * 8; idx += WM_DEC_THREADS) {
+      *reinterpret_cast<uint4*>(sK + (nk + (idx >> 3)) * 72 + (idx & 7) * 8) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sV + (nk + (idx >> 3)) * 72 + (idx & 7) * 8) = make_uint4(0, 0, 0, 0);
+    }
+    // queries (fp32) -> fp16 hi / lo, rows >= T are zero
+    for (int idx = tid; idx < 16 * 32; idx += WM_DEC_THREADS) {
+      const int r = idx >> 5, c2 = (idx & 31) * 2;
+      float a = 0.f, b = 0.f;
+      if (r < T) { const float2 v = *reinterpret_cast<const float2*>(m->q + (size_t)r * d + h * 64 + c2); a = v.x; b = v.y; }
+      uint32_t hi, lo;
+      split_hilo(a, b, hi, lo);
+      *reinterpret_cast<uint32_t*>(sQh + r * 72 + c2) = hi;
+      *reinterpret_cast<uint32_t*>(sQl + r * 72 + c2) = lo;
     }
     cta_sync();
-    if (t < T) {
-      for (int jj = pI; jj < nk; jj += P)
-        sS[t * WM_CH_MAX + jj] = dot64_h(q, reinterpret_cast<const uint4*>(sK + jj * 72)) * 0.125f;   // head_dim^-0.5
-    }
-    cta_sync();
-    // per-row max / exp / sum : warp per row
-    for (int r = warp; r < T; r += nwarps) {
-      float mx = -INFINITY;
-      for (int jj = lane; jj < nk; jj += 32) mx = fmaxf(mx, sS[r * WM_CH_MAX + jj]);
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int jj = lane; jj < nk; jj += 32) {
-        const float p = expf(sS[r * WM_CH_MAX + jj] - mx);
-        sS[r * WM_CH_MAX + jj] = p;
-        sum += p;
-      }
-      sum = warp_sum(sum);
-      if (lane == 0) { sM[r] = mx; sM[WM_MAX_T + r] = sum; }
-    }
-    cta_sync();
-    // P * V : thread = (key slice ks, row r, dim group dg); partial sums per key slice in shared memory
+    // ---- S = Q K^T * head_dim^-0.5 : warp w takes key tiles (8 keys) w, w + nwarps, ... ----
     {
-      int KS = WM_DEC_THREADS / (T * 8);
-      if (KS > 60) KS = 60;
-      const int ks = tid / (T * 8), rem = tid - ks * (T * 8);
-      const int r = rem >> 3, dg = rem & 7;
-      float a[8];
+      uint32_t qh[4][4], ql[4][4];
+      const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) a[e] = 0.f;
-      if (ks < KS) {
-        for (int jj = ks; jj < nk; jj += KS) {
-          const uint4 vv = *reinterpret_cast<const uint4*>(sV + jj * 64 + dg * 8);
-          const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
-          const float p = sS[r * WM_CH_MAX + jj];
+      for (int kk = 0; kk < 4; ++kk) {
+        const int ch = kk * 2 + (lane >> 4);
+        ldmatrix_x4(qh[kk][0], qh[kk][1], qh[kk][2], qh[kk][3], sQh + arow * 72 + ch * 8);
+        ldmatrix_x4(ql[kk][0], ql[kk][1], ql[kk][2], ql[kk][3], sQl + arow * 72 + ch * 8);
+      }
+      for (int nt = warp; nt < nk_pad / 8; nt += nwarps) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = __half22float2(v2[e]);
-            a[2 * e] = fmaf(p, f.x, a[2 * e]);
-            a[2 * e + 1] = fmaf(p, f.y, a[2 * e + 1]);
-          }
+        for (int k2 = 0; k2 < 2; ++k2) {
+          uint32_t b0, b1, b2, b3;   // (keys nt*8.., k-steps 2*k2 and 2*k2+1)
+          ldmatrix_x4(b0, b1, b2, b3, sK + (nt * 8 + (lane & 7)) * 72 + (k2 * 4 + (lane >> 3)) * 8);
+          mma_16816(acc, qh[2 * k2][0], qh[2 * k2][1], qh[2 * k2][2], qh[2 * k2][3], b0, b1);
+          mma_16816(acc, ql[2 * k2][0], ql[2 * k2][1], ql[2 * k2][2], ql[2 * k2][3], b0, b1);
+          mma_16816(acc, qh[2 * k2 + 1][0], qh[2 * k2 + 1][1], qh[2 * k2 + 1][2], qh[2 * k2 + 1][3], b2, b3);
+          mma_16816(acc, ql[2 * k2 + 1][0], ql[2 * k2 + 1][1], ql[2 * k2 + 1][2], ql[2 * k2 + 1][3], b2, b3);
         }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sAcc[((size_t)ks * T + r) * 64 + dg * 8 + e] = a[e];   // sK is dead by now
+        float* s0 = sS + gq * WM_CH_PAD + nt * 8 + 2 * tq;
+        s0[0] = acc[0] * 0.125f; s0[1] = acc[1] * 0.125f;
+        s0[8 * WM_CH_PAD] = acc[2] * 0.125f; s0[8 * WM_CH_PAD + 1] = acc[3] * 0.125f;
       }
-      cta_sync();
-      for (int idx = tid; idx < T * 64; idx += WM_DEC_THREADS) {
-        const int rr = idx >> 6, cc = idx & 63;
-        float o = 0.f;
-        for (int k2 = 0; k2 < KS; ++k2) o += sAcc[((size_t)k2 * T + rr) * 64 + cc];
-        m->cross_part[((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + rr) * (WM_HEAD_DIM + 2) + cc] = o;
+    }
+    cta_sync();
+    // ---- per-row max / exp / sum : warp per row; rows >= T and keys >= nk become zero probability ----
+    for (int r = warp; r < 16; r += nwarps) {
+      float* p = sS + r * WM_CH_PAD;
+      if (r < T) {
+        float mx = -INFINITY;
+        for (int jj = lane; jj < nk; jj += 32) mx = fmaxf(mx, p[jj]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int jj = lane; jj < nk_pad; jj += 32) {
+          const float e = (jj < nk) ? expf(p[jj] - mx) : 0.f;
+          p[jj] = e;
+          sum += e;
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) { sM[r] = mx; sM[WM_MAX_T + r] = sum; }
+      } else {
+        for (int jj = lane; jj < nk_pad; jj += 32) p[jj] = 0.f;
       }
-      if (tid < T) {
-        float* out = m->cross_part + ((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + tid) * (WM_HEAD_DIM + 2);
-        out[64] = sM[tid];
-        out[65] = sM[WM_MAX_T + tid];
+    }
+    cta_sync();
+    // ---- O = P V : warp w < 8 owns output dims w*8 .. w*8+7, all key steps ----
+    if (warp < 8) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int ks = 0; ks < nk_pad / 16; ++ks) {
+        const float* p0 = sS + gq * WM_CH_PAD + ks * 16 + 2 * tq;
+        const float2 a00 = *reinterpret_cast<const float2*>(p0);
+        const float2 a10 = *reinterpret_cast<const float2*>(p0 + 8 * WM_CH_PAD);
+        const float2 a01 = *reinterpret_cast<const float2*>(p0 + 8);
+        const float2 a11 = *reinterpret_cast<const float2*>(p0 + 8 * WM_CH_PAD + 8);
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split_hilo(a00.x, a00.y, h0, l0);   // row g,   keys 2t..2t+1
+        split_hilo(a10.x, a10.y, h1, l1);   // row g+8
+        split_hilo(a01.x, a01.y, h2, l2);   // row g,   keys 2t+8..
+        split_hilo(a11.x, a11.y, h3, l3);   // row g+8
+        uint32_t b0, b1;
+        ldmatrix_x2_trans(b0, b1, sV + (ks * 16 + (lane & 15)) * 72 + warp * 8);
+        mma_16816(acc, h0, h1, h2, h3, b0, b1);
+        mma_16816(acc, l0, l1, l2, l3, b0, b1);
       }
+      float* out0 = m->cross_part + ((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + gq) * (WM_HEAD_DIM + 2) + warp * 8 + 2 * tq;
+      if (gq < T) { out0[0] = acc[0]; out0[1] = acc[1]; }
+      if (gq + 8 < T) { out0[8 * (WM_HEAD_DIM + 2)] = acc[2]; out0[8 * (WM_HEAD_DIM + 2) + 1] = acc[3]; }
+    }
+    if (tid < T) {
+      float* out = m->cross_part + ((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + tid) * (WM_HEAD_DIM + 2);
+      out[64] = sM[tid];
+      out[65] = sM[WM_MAX_T + tid];
     }
     // fold: the chunk that arrives last for this head (always in chunk order => deterministic)
     __threadfence();
@@ -929,6 +975,9 @@ __device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mode, int l
   return g;
 }
 
+// WITH_GEMM = false: the caller runs the GEMM stages itself (ring kernel) -- keeps stage_gemm out of
+// that kernel's code
+template <bool WITH_GEMM = true>
 __device__ void run_stage(const DecModel* m, int stage, int mode, int layer, int cta, int ncta, unsigned char* smem,
                           const PassGeom* gopt = nullptr) {
   switch (stage) {
@@ -942,10 +991,11 @@ __device__ void run_stage(const DecModel* m, int stage, int mode, int layer, int
     case ST_SELECT2: stage_select2(m, cta, ncta, smem); break;
     case ST_SELECT_FIN: if (cta == 0) stage_select_fin(m, ncta); break;
     case ST_ACCEPT: if (cta == 0) stage_accept(m, ncta); break;
-    default: {
-      GemmDesc g = make_gemm_desc(m, stage, mode, layer, gopt);
-      stage_gemm(g, cta, ncta, smem);
-    }
+    default:
+      if (WITH_GEMM) {
+        GemmDesc g = make_gemm_desc(m, stage, mode, layer, gopt);
+        stage_gemm(g, cta, ncta, smem);
+      }
   }
 }
 

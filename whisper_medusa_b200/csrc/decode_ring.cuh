@@ -176,30 +176,31 @@ __device__ __forceinline__ void store_hilo4(__half* hi, __half* lo, float4 y) {
 
 #define WM_LN_MAXV 10   // float4 per lane: d <= 1280 (every Whisper size)
 
-__device__ __noinline__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __half* xlo, int xstride, int& rows_dirty) {
+__device__ __forceinline__ void ring_stage_x(const GemmDesc& g, int seg, int d, __half* xhi, __half* xlo, int xstride, int& rows_dirty) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = WM_DEC_THREADS >> 5;
   const int T = g.x_rows;
-  if (g.xsrc == XS_LN) {
-    const int nv = d >> 7;   // float4 per lane
-    const float4* g4 = reinterpret_cast<const float4*>(g.ln_g);
-    const float4* b4 = reinterpret_cast<const float4*>(g.ln_b);
-    if (warp < T) {
-      // the affine parameters are only needed after two reductions: pull them into L1 meanwhile
+  const int nv = d >> 7;   // float4 per lane
+  const bool ln = (g.xsrc == XS_LN);
+  const float4* g4 = reinterpret_cast<const float4*>(g.ln_g);
+  const float4* b4 = reinterpret_cast<const float4*>(g.ln_b);
+  if (ln && warp < T) {
+    // the affine parameters are only needed after two reductions: pull them into L1 meanwhile
+    for (int i = 0; i < nv; ++i) { prefetch_l1(g4 + i * 32 + lane); prefetch_l1(b4 + i * 32 + lane); }
+  }
+  // one warp per row: lane l holds float4 columns l, l+32, ...  (all loads in flight before first use)
+  for (int r = warp; r < T; r += nwarps) {
+    const float4* x4 = reinterpret_cast<const float4*>(g.X + (size_t)(g.x_row0 + r) * g.K + (size_t)seg * d);
+    float4 v[WM_LN_MAXV];
 #pragma unroll
-      for (int i = 0; i < WM_LN_MAXV; ++i)
-        if (i < nv) { prefetch_l1(g4 + i * 32 + lane); prefetch_l1(b4 + i * 32 + lane); }
-    }
-    for (int r = warp; r < T; r += nwarps) {
-      const float4* x4 = reinterpret_cast<const float4*>(g.X + (size_t)(g.x_row0 + r) * d);
-      float4 v[WM_LN_MAXV];
-#pragma unroll
-      for (int i = 0; i < WM_LN_MAXV; ++i)
-        if (i < nv) v[i] = x4[i * 32 + lane];
+    for (int i = 0; i < WM_LN_MAXV; ++i)
+      if (i < nv) v[i] = x4[i * 32 + lane];
+    float mean = 0.f, rstd = 1.f;
+    if (ln) {
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < WM_LN_MAXV; ++i)
         if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-      const float mean = warp_sum(s) / (float)d;
+      mean = warp_sum(s) / (float)d;
       float q = 0.f;
 #pragma unroll
       for (int i = 0; i < WM_LN_MAXV; ++i)
@@ -207,42 +208,23 @@ __device__ __noinline__ void ring_stage_x(const GemmDesc& g, int seg, int d, __h
           const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
           q += (a * a + b * b) + (c * c + e * e);
         }
-      const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+      rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+    }
+    __half* hi = xhi + (size_t)r * xstride + lane * 4;
+    __half* lo = xlo + (size_t)r * xstride + lane * 4;
 #pragma unroll
-      for (int i = 0; i < WM_LN_MAXV; ++i)
-        if (i < nv) {
+    for (int i = 0; i < WM_LN_MAXV; ++i)
+      if (i < nv) {
+        float4 y = v[i];
+        if (ln) {
           const float4 gg = g4[i * 32 + lane], bb = b4[i * 32 + lane];
-          float4 y;
           y.x = (v[i].x - mean) * rstd * gg.x + bb.x;
           y.y = (v[i].y - mean) * rstd * gg.y + bb.y;
           y.z = (v[i].z - mean) * rstd * gg.z + bb.z;
           y.w = (v[i].w - mean) * rstd * gg.w + bb.w;
-          const int col = (i * 32 + lane) * 4;
-          store_hilo4(xhi + (size_t)r * xstride + col, xlo + (size_t)r * xstride + col, y);
         }
-    }
-  } else {
-    const int d4 = d >> 2;
-    const int total = T * d4;
-    for (int base = 0; base < total; base += 8 * WM_DEC_THREADS) {
-      float4 v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = base + i * WM_DEC_THREADS + tid;
-        if (idx < total) {
-          const int r = idx / d4, c4 = idx - r * d4;
-          v[i] = *reinterpret_cast<const float4*>(g.X + (size_t)(g.x_row0 + r) * g.K + (size_t)seg * d + c4 * 4);
-        }
+        store_hilo4(hi + i * 128, lo + i * 128, y);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = base + i * WM_DEC_THREADS + tid;
-        if (idx < total) {
-          const int r = idx / d4, c4 = idx - r * d4;
-          store_hilo4(xhi + (size_t)r * xstride + c4 * 4, xlo + (size_t)r * xstride + c4 * 4, v[i]);
-        }
-      }
-    }
   }
   // rows that still hold data of an earlier, taller stage must read as zero
   if (rows_dirty > T) {
@@ -257,7 +239,7 @@ __device__ __noinline__ void ring_stage_x(const GemmDesc& g, int seg, int d, __h
 // ---------------------------------------------------------------------------------------------
 // GEMM stage fed from the ring (compute warps)
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, const GemmDesc& g, __half* xhi, __half* xlo, float* partial,
+__device__ __forceinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, const GemmDesc& g, __half* xhi, __half* xlo, float* partial,
                                 int& rows_dirty, unsigned long long* pr) {
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -283,7 +265,8 @@ __device__ __noinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, con
   const int rloc = j_ * 8 + 2 * (ln_ & 3) + (i_ & 1);
   // residual epilogue: fetch the old value while the MMAs run (single-unit stages only)
   float old = 0.f;
-  const bool pre_old = (g.epi == EPI_RESID) && !ksplit && units == 1 && tid < 256 && token < T && rloc < n_rows;
+  const bool mine = tid < 256 && token < T;
+  const bool pre_old = (g.epi == EPI_RESID) && !ksplit && units == 1 && mine && rloc < n_rows;
   if (pre_old) old = g.out[(size_t)token * g.ldo + n_begin + rloc];
   cta_sync();
   if (pr) pr[3] = global_timer_ns();
@@ -291,6 +274,9 @@ __device__ __noinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, con
     const unsigned int c = rc.consumed;
     const int slot = c % WM_RING_G;
     const int nvalid = min(16, n_rows - u * 16);
+    // this thread's bias for the unit: in flight while the MMAs run
+    float bias_v = 0.f;
+    if (mine && rloc < nvalid && g.bias && !ksplit) bias_v = g.bias[n_begin + u * 16 + rloc];
     while (!mbar_try_wait(rc.full + slot, (c / WM_RING_G) & 1)) { }
     if (pr && u == 0) pr[4] = global_timer_ns();
     if (warp < nks) {
@@ -332,16 +318,27 @@ __device__ __noinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, con
     if (pr && u == 0) pr[5] = global_timer_ns();
     rc.consumed = c + 1;
     if (tid == 0) mbar_arrive(rc.empty + slot);   // hand the slot back to the producer
-    if (tid < 256 && token < T && rloc < nvalid) {
+    if (mine && rloc < nvalid) {
       float s = 0.f;
       for (int ks = 0; ks < nks; ++ks) s += partial[(size_t)ks * 256 + tid];
       const int row = n_begin + u * 16 + rloc;
+      // common epilogues inline (bias was fetched while the MMAs ran); the Medusa-head ones are rare
       if (ksplit) {
         m->gemm_part[((size_t)wk.seg * 16 + token) * g.N + row] = s;
-      } else if (pre_old) {
-        g.out[(size_t)token * g.ldo + row] = old + (s + (g.bias ? g.bias[row] : 0.f));
+      } else if (g.epi == EPI_RESID) {
+        float* o = g.out + (size_t)token * g.ldo + row;
+        *o = (pre_old ? old : *o) + (s + bias_v);
+      } else if (g.epi == EPI_STORE || g.epi == EPI_LOGITS) {
+        g.out[(size_t)token * g.ldo + row] = s + bias_v;
+      } else if (g.epi == EPI_GELU) {
+        g.out[(size_t)token * g.ldo + row] = gelu_erf(s + bias_v);
+      } else if (g.epi == EPI_QKV) {
+        const float v = s + bias_v;
+        if (row < d) g.out[(size_t)token * g.ldo + row] = v;
+        else if (row < 2 * d) g.kc[(size_t)(g.base + token) * d + (row - d)] = __float2half_rn(v);
+        else g.vc[(size_t)(g.base + token) * d + (row - 2 * d)] = __float2half_rn(v);
       } else {
-        gemm_epilogue(g, token, row, s, xhi, xlo, xstride);
+        gemm_epilogue_heads(g.epi, g.out, g.ldo, g.out_row0, d, bias_v, token, row, s, xhi, xlo, xstride);
       }
     }
     cta_sync();   // partial buffer reusable
@@ -363,7 +360,8 @@ __device__ __noinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, con
         const int t = idx / n_rows, row = n_begin + (idx - t * n_rows);
         float s = 0.f;
         for (int sg = 0; sg < wk.segs; ++sg) s += __ldcg(m->gemm_part + ((size_t)sg * 16 + t) * g.N + row);
-        gemm_epilogue(g, t, row, s, xhi, xlo, xstride);
+        // K-split stages are residual GEMMs (FC2)
+        g.out[(size_t)t * g.ldo + row] += s + (g.bias ? g.bias[row] : 0.f);
       }
     }
   }
@@ -461,7 +459,7 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
       GemmDesc g = make_gemm_desc(m, in.stage, in.mode, in.layer, pg);
       stage_gemm_ring(rc, m, g, xhi, xlo, partial, rows_dirty, pr);
     } else {
-      run_stage(m, in.stage, in.mode, in.layer, cta, ncta, scratch_p, pg);
+      run_stage<false>(m, in.stage, in.mode, in.layer, cta, ncta, scratch_p, pg);
       // attention / scan stages overlay the activation slice: everything there is dirty now
       if (in.stage == ST_SELF_ATTN || in.stage == ST_CROSS_ATTN || in.stage == ST_SELECT1 || in.stage == ST_SELECT2)
         rows_dirty = 16;
