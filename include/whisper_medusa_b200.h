@@ -124,9 +124,10 @@ int wm_set_decode_mode(wm_handle* h, int32_t mode);
  * encoder GEMM. */
 int wm_set_option(wm_handle* h, const char* key, int32_t value);
 /* Debug: per-stage timeline of the last persistent iteration (after wm_set_option(h, "profile", 1)).
- * Rows of 11 int64: stage id, mode, layer, body ns and barrier-wait ns seen by CTA 0, then by the
- * last CTA, then (GEMM stages) ns offsets from stage begin on CTA 0 of: activations staged, first
- * weight chunk present, its MMAs done, its epilogue done. */
+ * Rows of 16 int64: stage id, mode, layer, body ns and barrier-wait ns seen by CTA 0, then by the
+ * last CTA, then (GEMM stages) ns offsets from stage begin on CTA 0 of: descriptor built, first
+ * activation row loaded, its LayerNorm statistics done, staging loop left, activations staged, first
+ * weight chunk present, its MMAs done, its epilogue done; one spare. */
 int wm_get_stage_profile(wm_handle* h, int64_t* out, int32_t cap_rows, int32_t* n_rows);
 
 #ifdef __cplusplus

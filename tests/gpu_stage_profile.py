@@ -38,6 +38,12 @@ def main():
     model.set_decode_mode("persistent")
     if "--tc" in sys.argv:
         model.set_option("enc_gemm", 1)
+    if "--no-prof" in sys.argv:     # plain run (e.g. under ncu): no timeline
+        pcm = synthetic_audio(30.0 if preset == "large-v2" else 5.0)
+        model.generate_from_pcm(pcm, language="en" if cfg.is_multilingual else None, max_iters=iters)
+        print(f"decode {model.last_trace.ms_decode:.3f} ms for {model.last_trace.iterations} iterations")
+        model.close()
+        return
     model.set_option("profile", 1)
     pcm = synthetic_audio(30.0 if preset == "large-v2" else 5.0)
     lang = "en" if cfg.is_multilingual else None
@@ -45,27 +51,30 @@ def main():
     tr = model.last_trace
     lib = _lib.load()
     cap = 4096
-    buf = (C.c_int64 * (cap * 11))()
+    buf = (C.c_int64 * (cap * 16))()
     n = C.c_int32(0)
     rc = lib.wm_get_stage_profile(model._handle, buf, cap, C.byref(n))
     assert rc == 0, lib.wm_last_error(model._handle)
-    rows = np.frombuffer(buf, dtype=np.int64)[: n.value * 11].reshape(-1, 11)
+    rows = np.frombuffer(buf, dtype=np.int64)[: n.value * 16].reshape(-1, 16)
     agg = OrderedDict()
-    for st, mode, layer, b0, w0, b1, w1, p0, p1, p2, p3 in rows:
-        a = agg.setdefault((STAGES[st], MODES[mode]), [0, 0, 0, 0, 0, 0, 0, 0, 0])
+    for row in rows:
+        st, mode, layer, b0, w0, b1, w1 = row[:7]
+        a = agg.setdefault((STAGES[st], MODES[mode]), [0] * 13)
         a[0] += 1; a[1] += b0; a[2] += w0; a[3] += b1; a[4] += w1
-        a[5] += max(p0, 0); a[6] += max(p1, 0); a[7] += max(p2, 0); a[8] += max(p3, 0)
+        for k in range(8):
+            a[5 + k] += max(row[7 + k], 0)
     print(f"{preset} K={heads} iterations={tr.iterations} decode {tr.ms_decode:.3f} ms "
           f"({tr.ms_decode / max(1, tr.iterations):.3f} ms/iter), encoder {tr.ms_encoder:.3f} ms, mel {tr.ms_mel:.3f} ms")
-    print(f"{'stage':<14}{'mode':<6}{'n':>4}{'body0 us':>10}{'wait0 us':>10}{'bodyN us':>10}{'waitN us':>10}{'total us':>10}"
-          f"{'x-staged':>10}{'w-ready':>10}{'mma-done':>10}{'epi-done':>10}")
+    sub = ["desc", "x-load", "ln-stat", "x-loop", "x-sync", "w-ready", "mma", "epi"]
+    print(f"{'stage':<12}{'mode':<5}{'n':>3}{'body0':>7}{'wait0':>7}{'bodyN':>7}{'waitN':>7}{'total':>8}"
+          + "".join(f"{x:>8}" for x in sub) + "   (us; sub-phases = offsets from stage begin, CTA 0)")
     tot = 0.0
-    for (st, mode), (cnt, b0, w0, b1, w1, p0, p1, p2, p3) in agg.items():
-        t = (b0 + w0) / 1e3
+    for (st, mode), a in agg.items():
+        cnt = a[0]
+        t = (a[1] + a[2]) / 1e3
         tot += t
-        print(f"{st:<14}{mode:<6}{cnt:>4}{b0 / cnt / 1e3:>10.2f}{w0 / cnt / 1e3:>10.2f}{b1 / cnt / 1e3:>10.2f}"
-              f"{w1 / cnt / 1e3:>10.2f}{t:>10.1f}{p0 / cnt / 1e3:>10.2f}{p1 / cnt / 1e3:>10.2f}{p2 / cnt / 1e3:>10.2f}"
-              f"{p3 / cnt / 1e3:>10.2f}")
+        print(f"{st:<12}{mode:<5}{cnt:>3}{a[1] / cnt / 1e3:>7.2f}{a[2] / cnt / 1e3:>7.2f}{a[3] / cnt / 1e3:>7.2f}"
+              f"{a[4] / cnt / 1e3:>7.2f}{t:>8.1f}" + "".join(f"{a[5 + k] / cnt / 1e3:>8.2f}" for k in range(8)))
     print(f"sum over stages of the last iteration (CTA 0): {tot / 1e3:.3f} ms")
     model.close()
 

@@ -21,6 +21,28 @@ struct ChunkDesc {
   uint32_t nrows;
 };
 
+// One stage of the persistent ring kernel, fully resolved for one CTA by the host (built once per
+// model, [instruction][cta], 128 B each): the kernel never derives shapes, row ranges or pointers on
+// the critical path -- it prefetches the next record into shared memory while the current stage runs.
+struct alignas(16) CtaStage {
+  int stage, mode, layer;   // StageId, pass mode, decoder layer
+  int epi;                  // GEMM stages: epilogue kind
+  const float* X;           // activation rows (fp32), already offset by x_row0 and the k segment
+  const float* bias;        // [N] or null
+  const float* ln_g;        // LayerNorm of the activations (null: plain)
+  const float* ln_b;
+  float* out;
+  __half* kc;               // EPI_QKV: self K/V cache of the layer
+  __half* vc;
+  const void* pf[2];        // vectors worth pulling into L2 for the NEXT LayerNorm stage (its ln_g, ln_b)
+  int x_ld;                 // row stride of X in floats
+  int x_rows_fixed;         // 0: the pass's T rows
+  int n_begin, n_rows;      // W rows of this CTA
+  int N, ldo, out_row0;
+  int segs, seg, block;     // K split (FC2): segs > 1
+};
+static_assert(sizeof(CtaStage) == 128, "CtaStage must be one 128-byte line");
+
 // Barrier over the WM_DEC_THREADS compute threads of a decode CTA.  The persistent ring kernel has
 // one extra warp (the weight producer) that never joins it, hence a named barrier instead of
 // __syncthreads(); in the 512-thread kernels it is simply "all threads".
@@ -58,6 +80,26 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
+}
+
+// ---- cross-CTA data exchange without L1 invalidation -----------------------------------------
+// Everything one decode CTA writes for another (activations, new K/V rows, partials, loop state) is
+// READ with L2-coherent loads (ld.global.cg == __ldcg), never through L1.  The grid barrier and the
+// last-arriver counters then only need RELEASE semantics on the arriving side (MEMBAR + RED/ATOM);
+// no acquire fence, so no CCTL.IVALL: weights' LN/bias vectors, tables and local memory stay
+// L1-resident across the ~230 barriers of an iteration.
+__device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ int ldcg_i(const int* p) { return __ldcg(p); }
+__device__ __forceinline__ float2 ldcg_f2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ uint4 ldcg_u4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void red_add_release(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int atom_add_release(unsigned int* p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -177,6 +219,7 @@ struct DecModel {
   // chunk_tab[chunk_off[cta*4 + list] .. chunk_off[cta*4 + list + 1]) in consumption order
   const struct ChunkDesc* chunk_tab;
   const int* chunk_off;
+  const struct CtaStage* stage_tab;   // [prog_off[3]][n_sm] resolved stage records of the ring kernel
   DecState* st;
   unsigned int* bar;  // grid-barrier words for the persistent kernel
   unsigned long long* prof;  // optional stage timeline [2 CTAs][n_instr][3] (ns), null = off

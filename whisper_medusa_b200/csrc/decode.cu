@@ -51,12 +51,12 @@ __device__ __forceinline__ PassGeom pass_geom(const DecModel* m, int mode) {
 // -----------------------------------------------------------------------------------------
 // stage: token + position embedding  (HF modeling_whisper.py:737-763)
 // -----------------------------------------------------------------------------------------
-__device__ __noinline__ void stage_embed(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
+__device__ __forceinline__ void stage_embed(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
   const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const DecState* st = m->st;
   const int d = m->d;
   for (int t = cta; t < g.T; t += ncta) {
-    int tok = (mode == MODE_A) ? st->ids[g.base + t] : st->cand[t];
+    int tok = (mode == MODE_A) ? ldcg_i(&st->ids[g.base + t]) : ldcg_i(&st->cand[t]);
     const __half* e = m->embed + (size_t)tok * d;
     const float* p = m->pos + (size_t)(g.base + t) * d;
     float* x = m->x + (size_t)t * d;
@@ -367,7 +367,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
     const int nk_max = g.base + t0 + rg;           // keys of the last row of the group
     cta_sync();
     for (int idx = tid; idx < rg * 64; idx += WM_DEC_THREADS)
-      s_q[idx] = m->q[(size_t)(t0 + (idx >> 6)) * d + h * 64 + (idx & 63)];
+      s_q[idx] = ldcg_f(&m->q[(size_t)(t0 + (idx >> 6)) * d + h * 64 + (idx & 63)]);
     cta_sync();
     // scores (scaled by head_dim^-0.5; HF scales q, a power of two, so this is identical)
     const int npairs = rg * nk_max;
@@ -376,7 +376,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
       const uint4* k0 = reinterpret_cast<const uint4*>(L.self_k + (size_t)j0 * d + h * 64);
       uint4 a[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[c] = k0[c];
+      for (int c = 0; c < 8; ++c) a[c] = ldcg_u4(k0 + c);
       const bool ok0 = j0 <= g.base + t0 + r0;     // causal
       s_p[r0 * WM_MAX_POS + j0] = ok0 ? dot64_h(s_q + r0 * 64, a) * 0.125f : -INFINITY;
     }
@@ -407,7 +407,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
         const float* p = s_p + r * WM_MAX_POS;
 #pragma unroll 4
         for (int jj = kg; jj < nk; jj += KG) {
-          const uint4 vv = *reinterpret_cast<const uint4*>(L.self_v + (size_t)jj * d + h * 64 + dg * 8);
+          const uint4 vv = ldcg_u4(L.self_v + (size_t)jj * d + h * 64 + dg * 8);
           const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
           const float pj = p[jj];
 #pragma unroll
@@ -502,7 +502,7 @@ __device__ __forceinline__ void stage_cross_attn(const DecModel* m, int mode, in
     for (int idx = tid; idx < 16 * 32; idx += WM_DEC_THREADS) {
       const int r = idx >> 5, c2 = (idx & 31) * 2;
       float a = 0.f, b = 0.f;
-      if (r < T) { const float2 v = *reinterpret_cast<const float2*>(m->q + (size_t)r * d + h * 64 + c2); a = v.x; b = v.y; }
+      if (r < T) { const float2 v = ldcg_f2(m->q + (size_t)r * d + h * 64 + c2); a = v.x; b = v.y; }
       uint32_t hi, lo;
       split_hilo(a, b, hi, lo);
       *reinterpret_cast<uint32_t*>(sQh + r * 72 + c2) = hi;
@@ -585,16 +585,15 @@ __device__ __forceinline__ void stage_cross_attn(const DecModel* m, int mode, in
       out[65] = sM[WM_MAX_T + tid];
     }
     // fold: the chunk that arrives last for this head (always in chunk order => deterministic)
-    __threadfence();
+    // (release-only arrival; the partials are read back with L2-coherent loads, see common.cuh)
     cta_sync();
     if (tid == 0) {
-      const unsigned int prev = atomicAdd(&m->cross_cnt[h], 1u);
+      const unsigned int prev = atom_add_release(&m->cross_cnt[h], 1u);
       s_last = (prev == (unsigned int)(nch - 1)) ? 1 : 0;
       if (s_last) m->cross_cnt[h] = 0u;   // everybody has arrived: re-arm for the next layer
     }
     cta_sync();
     if (s_last) {
-      __threadfence();
       const size_t cstride = (size_t)WM_MAX_T * (WM_HEAD_DIM + 2);
       for (int idx = tid; idx < T * 64; idx += WM_DEC_THREADS) {
         const int rr = idx >> 6, e = idx & 63;
@@ -619,7 +618,7 @@ __device__ __forceinline__ void stage_cross_attn(const DecModel* m, int mode, in
 //            input of the Medusa heads).  sweep B + block type: base logits read the hidden
 //            states directly (reference model.py:1287).
 // -----------------------------------------------------------------------------------------
-__device__ __noinline__ void stage_final_ln(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
+__device__ __forceinline__ void stage_final_ln(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
   const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const int d = m->d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -631,7 +630,7 @@ __device__ __noinline__ void stage_final_ln(const DecModel* m, int mode, int cta
     float4 v[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i)
-      if (i < nv) v[i] = x4[i * 32 + lane];
+      if (i < nv) v[i] = __ldcg(x4 + i * 32 + lane);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 10; ++i)
@@ -667,12 +666,12 @@ __device__ __noinline__ void stage_final_ln(const DecModel* m, int mode, int cta
 __device__ void stage_copy_hidden_to_x(const DecModel* m, int mode, int cta, int ncta, const PassGeom* gopt) {
   const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const int total = g.T * m->d;
-  for (int idx = cta * WM_DEC_THREADS + threadIdx.x; idx < total; idx += ncta * WM_DEC_THREADS) m->x[idx] = m->hidden[idx];
+  for (int idx = cta * WM_DEC_THREADS + threadIdx.x; idx < total; idx += ncta * WM_DEC_THREADS) m->x[idx] = ldcg_f(&m->hidden[idx]);
 }
 // block type, tail: the block runs on the carried hidden state (one row); vocab row 0 = base logits
 __device__ void stage_tail_seed(const DecModel* m, int cta, int ncta) {
   for (int idx = cta * WM_DEC_THREADS + threadIdx.x; idx < m->d; idx += ncta * WM_DEC_THREADS) {
-    const float y = m->carry[idx];
+    const float y = ldcg_f(&m->carry[idx]);
     m->x[idx] = y;
     m->head_h[idx] = y;
   }
@@ -688,7 +687,7 @@ __device__ __forceinline__ float processed_logit(const float* row, int j, const 
                                                  int eos, float pen) {
   const uint8_t mk = mask[j];
   if ((mk & 1) || (begin_on && (mk & 2))) return -INFINITY;
-  float v = row[j];
+  float v = ldcg_f(row + j);
   if (j == eos && pen != 0.f) v = v + fabsf(v) * pen;
   return v;
 }
@@ -813,7 +812,7 @@ __device__ __noinline__ void stage_select2(const DecModel* m, int cta, int ncta,
     ent = block_sum(ent, s_val);
     if (threadIdx.x == 0) {
       m->sel_part[((size_t)r * WM_SEL_MAXSEG + sg) * 4 + 3] = ent;
-      const int c = st->cand[r + 1];
+      const int c = ldcg_i(&st->cand[r + 1]);
       if (c >= j0 && c < j1)
         st->row_pc[r] = expf((processed_logit(row, c, m->tok_mask, begin_on, eos, pen) - M) * inv_t) / Z;
     }
@@ -868,13 +867,13 @@ __device__ __noinline__ void stage_accept(const DecModel* m, int ncta) {
     const int L = st->L;
     int a = 0;
     if (st->temperature == 0.f) {
-      while (a < K && st->cand[a + 1] == st->row_argmax[a]) ++a;
+      while (a < K && ldcg_i(&st->cand[a + 1]) == ldcg_i(&st->row_argmax[a])) ++a;
     } else {
-      while (a < K && st->row_pc[a] > st->row_thr[a]) ++a;
+      while (a < K && ldcg_f(&st->row_pc[a]) > ldcg_f(&st->row_thr[a])) ++a;
     }
     int n_new = a + 1;
-    for (int i = 0; i <= a; ++i) st->ids[L + i] = st->cand[i];
-    if (a == 0) { st->ids[L + 1] = st->row_argmax[0]; n_new = 2; }
+    for (int i = 0; i <= a; ++i) st->ids[L + i] = ldcg_i(&st->cand[i]);
+    if (a == 0) { st->ids[L + 1] = ldcg_i(&st->row_argmax[0]); n_new = 2; }
     bool eos = false;
     for (int i = 0; i < n_new; ++i) eos |= (st->ids[L + i] == st->eos);
     const int newL = L + n_new;
@@ -893,7 +892,7 @@ __device__ __noinline__ void stage_accept(const DecModel* m, int ncta) {
   const int a = s_a;
   if (a >= 1) {
     const float* src = m->hidden + (size_t)a * m->d;
-    for (int j = threadIdx.x; j < m->d; j += WM_DEC_THREADS) m->carry[j] = src[j];
+    for (int j = threadIdx.x; j < m->d; j += WM_DEC_THREADS) m->carry[j] = ldcg_f(src + j);
   }
 }
 
@@ -907,8 +906,14 @@ enum StageId {
 };
 enum PhaseId { PH_SWEEP_A = 0, PH_TAIL = 1, PH_VERIFY = 2 };
 
-__device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mode, int layer, const PassGeom* gopt) {
+// (host: called with the host copy of the model and an explicit geometry -- x_rows / base of the pass
+// are placeholders there, see dec_build_stage_table)
+__host__ __device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mode, int layer, const PassGeom* gopt) {
+#ifdef __CUDA_ARCH__
   const PassGeom pg = gopt ? *gopt : pass_geom(m, mode);
+#else
+  const PassGeom pg = *gopt;
+#endif
   GemmDesc g;
   const int d = m->d;
   g.d = d;
@@ -1045,25 +1050,34 @@ dec_stage_kernel(const DecModel* __restrict__ m, int stage, int mode, int layer,
 // -----------------------------------------------------------------------------------------
 // mode 1: persistent cooperative kernel -- one launch per speculative iteration
 // -----------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
   unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 // All CTAs are co-resident (cooperative launch).  bar[0] is a monotonically increasing arrival
 // counter (reset by the host before every wm_generate): barrier number e completes when it
-// reaches ncta * e.
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch, int ncta) {
+// reaches ncta * e.  Arrival is a release RED (MEMBAR.ALL.GPU + REDG), the poll a relaxed
+// (L2-coherent) load.  ACQUIRE = false (ring kernel): no fence after the poll -- every cross-CTA
+// read of that kernel is an L2-coherent load (common.cuh), so L1 need not be invalidated (ncu
+// showed CCTL.IVALL after each barrier turning every LN/bias/local-memory access into an L2 trip).
+template <bool ACQUIRE>
+__device__ __forceinline__ unsigned int grid_barrier_step(unsigned int* bar, unsigned int epoch, int ncta) {
+  // the ring kernel's consumers fetch activations with bulk async copies: order this thread's generic-proxy
+  // global writes before async-proxy reads that follow the barrier
+  if (!ACQUIRE) asm volatile("fence.proxy.async.global;" ::: "memory");
   cta_sync();
   if (threadIdx.x == 0) {
-    epoch += 1;
-    const unsigned int target = (unsigned int)ncta * epoch;
-    __threadfence();
-    atomicAdd(&bar[0], 1u);
-    while (ld_acquire_u32(&bar[0]) < target) { }
-    __threadfence();
+    const unsigned int target = (unsigned int)ncta * (epoch + 1u);
+    red_add_release(&bar[0], 1u);
+    while (ld_relaxed_u32(&bar[0]) < target) { }
+    if (ACQUIRE) __threadfence();
   }
   cta_sync();
+  return epoch + 1u;
+}
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch, int ncta) {
+  epoch = grid_barrier_step<true>(bar, epoch, ncta);
 }
 
 __global__ void __launch_bounds__(WM_DEC_THREADS, 1)
@@ -1140,10 +1154,49 @@ void dec_build_chunk_table(const DecModel& hm, int ncta, std::vector<ChunkDesc>&
   }
 }
 
-cudaError_t dec_launch_iteration_ring(const DecModel* dm, const DecHostInfo& hi, cudaStream_t s) {
+// Resolved stage records of the ring kernel: tab[ip * ncta + cta] (see CtaStage in common.cuh).
+void dec_build_stage_table(const DecModel& hm, int ncta, std::vector<CtaStage>& tab) {
+  std::vector<int> flat;
+  int poff[4];
+  dec_build_program(hm.n_layers, hm.has_block, flat, poff);
+  const int n = poff[3];
+  tab.assign((size_t)n * ncta, CtaStage{});
+  const PassGeom dyn{-1, 0};   // T = -1: "the rows of the pass" (resolved on the device)
+  for (int ip = 0; ip < n; ++ip) {
+    const int stage = flat[ip * 3], mode = flat[ip * 3 + 1], layer = flat[ip * 3 + 2];
+    // LayerNorm vectors of the next LN-fed GEMM stage in program order (L2 prefetch hint)
+    const void* pf0 = nullptr; const void* pf1 = nullptr;
+    for (int jp = ip + 1; jp < n && jp < ip + 6; ++jp) {
+      if (!is_gemm_stage(flat[jp * 3])) continue;
+      const GemmDesc gn = make_gemm_desc(&hm, flat[jp * 3], flat[jp * 3 + 1], flat[jp * 3 + 2], &dyn);
+      if (gn.xsrc == XS_LN) { pf0 = gn.ln_g; pf1 = gn.ln_b; break; }
+    }
+    for (int cta = 0; cta < ncta; ++cta) {
+      CtaStage& c = tab[(size_t)ip * ncta + cta];
+      c.stage = stage; c.mode = mode; c.layer = layer;
+      c.pf[0] = pf0; c.pf[1] = pf1;
+      if (!is_gemm_stage(stage)) continue;
+      const GemmDesc g = make_gemm_desc(&hm, stage, mode, layer, &dyn);
+      const GemmWork wk = gemm_work(g.N, g.K, hm.d, cta, ncta);
+      c.epi = g.epi;
+      c.X = g.X + (size_t)g.x_row0 * g.K + (size_t)wk.seg * hm.d;
+      c.x_ld = g.K;
+      c.x_rows_fixed = g.x_rows < 0 ? 0 : g.x_rows;
+      c.bias = g.bias;
+      c.ln_g = (g.xsrc == XS_LN) ? g.ln_g : nullptr;
+      c.ln_b = (g.xsrc == XS_LN) ? g.ln_b : nullptr;
+      c.out = g.out; c.kc = g.kc; c.vc = g.vc;
+      c.n_begin = wk.n_begin; c.n_rows = wk.n_rows;
+      c.N = g.N; c.ldo = g.ldo; c.out_row0 = g.out_row0;
+      c.segs = wk.segs; c.seg = wk.seg; c.block = wk.block;
+    }
+  }
+}
+
+cudaError_t dec_launch_iteration_ring(const DecModel* dm, const DecHostInfo& hi, bool profile, cudaStream_t s) {
   void* args[] = {(void*)&dm};
-  return cudaLaunchCooperativeKernel((void*)dec_iteration_ring_kernel, dim3(hi.n_sm), dim3(WM_RING_THREADS), args,
-                                     hi.smem_ring, s);
+  void* fn = profile ? (void*)dec_iteration_ring_kernel<true> : (void*)dec_iteration_ring_kernel<false>;
+  return cudaLaunchCooperativeKernel(fn, dim3(hi.n_sm), dim3(WM_RING_THREADS), args, hi.smem_ring, s);
 }
 
 size_t dec_smem_bytes(int d, int ffn) {
@@ -1160,7 +1213,9 @@ cudaError_t dec_configure(size_t smem, size_t smem_ring) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(dec_iteration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dec_iteration_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring);
+  e = cudaFuncSetAttribute(dec_iteration_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dec_iteration_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring);
 }
 
 static int stage_grid(int stage, int T, int n_sm, int H, int K) {

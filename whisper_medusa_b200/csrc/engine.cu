@@ -64,6 +64,7 @@ struct wm_handle {
   unsigned long long* prof = nullptr;
   ChunkDesc* chunk_tab = nullptr;
   int* chunk_off = nullptr;
+  CtaStage* stage_tab = nullptr;
   DecHostInfo hi;
   std::map<int, cudaGraphExec_t> graph_a;  // sweep A, keyed by T
   cudaGraphExec_t graph_tail = nullptr, graph_b = nullptr;
@@ -328,7 +329,7 @@ extern "C" int wm_destroy(wm_handle* h) {
   for (auto p : h->self_k) F(p);
   for (auto p : h->self_v) F(p);
   F(h->hm.x); F(h->hm.q); F(h->hm.attn); F(h->hm.ffn_h); F(h->hm.hidden); F(h->hm.head_h); F(h->hm.carry); F(h->hm.cross_part); F(h->hm.cross_cnt); F(h->hm.sel_part); F(h->hm.gemm_part); F(h->hm.gemm_cnt);
-  F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->prog); F(h->prof); F(h->chunk_tab); F(h->chunk_off); F(h->dm);
+  F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->prog); F(h->prof); F(h->chunk_tab); F(h->chunk_off); F(h->stage_tab); F(h->dm);
   if (h->wowned) F(h->wdev);
   if (h->h_state) cudaFreeHost(h->h_state);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -404,6 +405,12 @@ static int bind_weights(wm_handle* h) {
     CK(cudaMemcpy(h->chunk_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
     m.chunk_tab = h->chunk_tab;
     m.chunk_off = h->chunk_off;
+    std::vector<CtaStage> stab;
+    dec_build_stage_table(m, h->n_sm, stab);
+    if (h->stage_tab) { cudaFree(h->stage_tab); h->stage_tab = nullptr; }
+    CK(cudaMalloc((void**)&h->stage_tab, stab.size() * sizeof(CtaStage)));
+    CK(cudaMemcpy(h->stage_tab, stab.data(), stab.size() * sizeof(CtaStage), cudaMemcpyHostToDevice));
+    m.stage_tab = h->stage_tab;
   }
   CK(cudaMemcpy(h->dm, &m, sizeof m, cudaMemcpyHostToDevice));
   h->wready = true;
@@ -651,7 +658,7 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
         CK(dec_launch_iteration(h->dm, h->hi, s));
         h->launches[2] += 1;
       } else {
-        CK(dec_launch_iteration_ring(h->dm, h->hi, s));
+        CK(dec_launch_iteration_ring(h->dm, h->hi, h->hm.prof != nullptr, s));
         h->launches[2] += 1;
       }
     }
@@ -726,7 +733,7 @@ extern "C" int wm_set_option(wm_handle* h, const char* key, int32_t value) {
   if (k == "profile") {
     // stage timeline of the persistent ring kernel (debug): buffer [2][n_instr][3] u64
     CK(cudaSetDevice(h->device));
-    if (value && !h->prof) CK(dalloc(&h->prof, (size_t)2 * h->hm.prog_off[3] * 8));
+    if (value && !h->prof) CK(dalloc(&h->prof, (size_t)2 * h->hm.prog_off[3] * 16));
     h->hm.prof = value ? h->prof : nullptr;
     CK(cudaMemcpy(h->dm, &h->hm, sizeof(DecModel), cudaMemcpyHostToDevice));
     return WM_OK;
@@ -739,29 +746,32 @@ extern "C" int wm_set_option(wm_handle* h, const char* key, int32_t value) {
   }
   return fail(h, WM_ERR_INVALID, "unknown option " + k);
 }
-// Stage timeline of the last persistent-ring iteration (option "profile" = 1): rows of
+// Stage timeline of the last persistent-ring iteration (option "profile" = 1): rows of 16 int64
 // {stage, mode, layer, body_ns(cta 0), barrier_ns(cta 0), body_ns(last cta), barrier_ns(last cta),
-//  4 GEMM sub-phase offsets (ns since stage begin, CTA 0)}  -- 11 int64 per row
+//  8 GEMM sub-phase offsets (ns since stage begin, CTA 0), 0}
 extern "C" int wm_get_stage_profile(wm_handle* h, int64_t* out, int32_t cap_rows, int32_t* n_rows) {
   if (!h || !out || !n_rows) return WM_ERR_INVALID;
   if (!h->prof) return fail(h, WM_ERR_STATE, "profiling is off (wm_set_option(h, \"profile\", 1))");
   CK(cudaSetDevice(h->device));
   const int n = h->hm.prog_off[3];
-  std::vector<unsigned long long> raw((size_t)2 * n * 8);
+  std::vector<unsigned long long> raw((size_t)2 * n * 16);
   std::vector<int> prog((size_t)n * 3);
   CK(cudaMemcpy(raw.data(), h->prof, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(prog.data(), h->prog, prog.size() * sizeof(int), cudaMemcpyDeviceToHost));
   int rows = 0;
   for (int i = 0; i < n && rows < cap_rows; ++i) {
-    const unsigned long long* a = &raw[(size_t)i * 8];
-    const unsigned long long* b = &raw[((size_t)n + i) * 8];
-    if (a[0] == 0) continue;   // stage not executed in the last iteration (sweep A skipped)
-    int64_t* o = out + (size_t)rows * 11;
+    const unsigned long long* a = &raw[(size_t)i * 16];
+    const unsigned long long* b = &raw[((size_t)n + i) * 16];
+    if (a[0] == 0) continue;   // stage never executed (sweep A skipped)
+    int64_t* o = out + (size_t)rows * 16;
     o[0] = prog[i * 3]; o[1] = prog[i * 3 + 1]; o[2] = prog[i * 3 + 2];
     o[3] = (int64_t)(a[1] - a[0]); o[4] = (int64_t)(a[2] - a[1]);
     o[5] = (int64_t)(b[1] - b[0]); o[6] = (int64_t)(b[2] - b[1]);
-    // GEMM stages (CTA 0): X staged, first chunk ready, first chunk MMAs done, first chunk epilogue done
-    for (int k = 0; k < 4; ++k) o[7 + k] = a[3 + k] >= a[0] ? (int64_t)(a[3 + k] - a[0]) : -1;
+    // GEMM stages (CTA 0): descriptor built, X row loaded, LN statistics done, X staged + synced, staging loop
+    // left, first chunk ready, first chunk MMAs done, first chunk epilogue done
+    static const int order[8] = {7, 8, 9, 10, 3, 4, 5, 6};
+    for (int k = 0; k < 8; ++k) { const unsigned long long v = a[order[k]]; o[7 + k] = v >= a[0] ? (int64_t)(v - a[0]) : -1; }
+    o[15] = 0;
     ++rows;
   }
   *n_rows = rows;

@@ -24,7 +24,9 @@ size_t dec_ring_smem_bytes(int d);
 void dec_build_program(int n_layers, int has_block, std::vector<int>& flat, int off[4]);
 struct ChunkDesc;
 void dec_build_chunk_table(const DecModel& hm, int ncta, std::vector<ChunkDesc>& tab, std::vector<int>& off);
-cudaError_t dec_launch_iteration_ring(const DecModel* dm, const DecHostInfo& hi, cudaStream_t s);
+struct CtaStage;
+void dec_build_stage_table(const DecModel& hm, int ncta, std::vector<CtaStage>& tab);
+cudaError_t dec_launch_iteration_ring(const DecModel* dm, const DecHostInfo& hi, bool profile, cudaStream_t s);
 // phase: 0 = sweep A over T uncached rows, 1 = tail (candidates), 2 = verify sweep + accept
 cudaError_t dec_enqueue_phase(const DecModel* dm, const DecHostInfo& hi, int phase, int T, cudaStream_t s, int64_t* n_launch);
 cudaError_t dec_launch_iteration(const DecModel* dm, const DecHostInfo& hi, cudaStream_t s);
