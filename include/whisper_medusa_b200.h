@@ -124,10 +124,12 @@ int wm_set_decode_mode(wm_handle* h, int32_t mode);
  * encoder GEMM. */
 int wm_set_option(wm_handle* h, const char* key, int32_t value);
 /* Debug: per-stage timeline of the last persistent iteration (after wm_set_option(h, "profile", 1)).
- * Rows of 16 int64: stage id, mode, layer, body ns and barrier-wait ns seen by CTA 0, then by the
- * last CTA, then (GEMM stages) ns offsets from stage begin on CTA 0 of: descriptor built, first
- * activation row loaded, its LayerNorm statistics done, staging loop left, activations staged, first
- * weight chunk present, its MMAs done, its epilogue done; one spare. */
+ * Rows of 24 int64: stage id, mode, layer; body ns and barrier-wait ns seen by the last CTA; then the
+ * 16 raw probes of CTA 0 -- ns offsets from stage begin ([1] end of body, [2] end of barrier, [7] record
+ * read, [8] activations landed, [9] LayerNorm statistics, [10] split done, [3] staged, [13] before the
+ * weight wait, [4] weights present, [5] MMAs done, [6] epilogue done, [14] unit loop left, [15] stage
+ * function left) and two flags ([11], [12]: weights already present at stage begin / before the wait);
+ * 3 spare. */
 int wm_get_stage_profile(wm_handle* h, int64_t* out, int32_t cap_rows, int32_t* n_rows);
 
 #ifdef __cplusplus

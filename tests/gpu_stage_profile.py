@@ -1,6 +1,6 @@
 """Per-stage timeline of the persistent decode kernel (device %globaltimer, CTA 0 and last CTA).
 
-    python tests/gpu_stage_profile.py [--preset large-v2] [--heads 10] [--block] [--iters 6] [--tc]
+    python tests/gpu_stage_profile.py [--preset large-v2] [--heads 10] [--block] [--iters 6] [--tc] [--temp0] [--seed 0]
 
 Prints, per stage type, the mean body time and barrier-wait time over the layers of the LAST
 iteration, and the critical-path sum.  Used to decide what to optimise next (profiles/*.txt).
@@ -34,47 +34,59 @@ def main():
     heads = arg("--heads", 10)
     iters = arg("--iters", 6)
     cfg = preset_config(preset, heads=heads, heads_type="medusa_block" if "--block" in sys.argv else "base_head")
-    model = WhisperMedusaModel(cfg, synthetic_state_dict(cfg, seed=0)).to("cuda:0")
+    for _ in range(arg("--warm-instances", 0)):   # earlier engine instances in the same process (then closed)
+        w = WhisperMedusaModel(cfg, synthetic_state_dict(cfg, seed=arg("--seed", 0))).to("cuda:0")
+        w.set_decode_mode("persistent")
+        w.generate_from_pcm(synthetic_audio(5.0), language="en" if cfg.is_multilingual else None, max_iters=iters,
+                            **({"medusa_temperature": 0.0} if "--temp0" in sys.argv else {}))
+        print(f"warm instance: decode {w.last_trace.ms_decode:.3f} ms for {w.last_trace.iterations} iterations")
+        if "--keep" not in sys.argv:
+            w.close()
+    model = WhisperMedusaModel(cfg, synthetic_state_dict(cfg, seed=arg("--seed", 0))).to("cuda:0")
+    gen_kw = {"medusa_temperature": 0.0} if "--temp0" in sys.argv else {}
     model.set_decode_mode("persistent")
     if "--tc" in sys.argv:
         model.set_option("enc_gemm", 1)
     if "--no-prof" in sys.argv:     # plain run (e.g. under ncu): no timeline
         pcm = synthetic_audio(30.0 if preset == "large-v2" else 5.0)
-        model.generate_from_pcm(pcm, language="en" if cfg.is_multilingual else None, max_iters=iters)
+        model.generate_from_pcm(pcm, language="en" if cfg.is_multilingual else None, max_iters=iters, **gen_kw)
         print(f"decode {model.last_trace.ms_decode:.3f} ms for {model.last_trace.iterations} iterations")
         model.close()
         return
     model.set_option("profile", 1)
     pcm = synthetic_audio(30.0 if preset == "large-v2" else 5.0)
     lang = "en" if cfg.is_multilingual else None
-    model.generate_from_pcm(pcm, language=lang, max_iters=iters)
+    model.generate_from_pcm(pcm, language=lang, max_iters=iters, **gen_kw)
     tr = model.last_trace
     lib = _lib.load()
     cap = 4096
-    buf = (C.c_int64 * (cap * 16))()
+    buf = (C.c_int64 * (cap * 24))()
     n = C.c_int32(0)
     rc = lib.wm_get_stage_profile(model._handle, buf, cap, C.byref(n))
     assert rc == 0, lib.wm_last_error(model._handle)
-    rows = np.frombuffer(buf, dtype=np.int64)[: n.value * 16].reshape(-1, 16)
+    rows = np.frombuffer(buf, dtype=np.int64)[: n.value * 24].reshape(-1, 24)
+    # probes in timeline order (see include/whisper_medusa_b200.h)
+    order = [7, 8, 9, 10, 3, 13, 4, 5, 6, 14, 15, 1, 2]
+    names = ["desc", "x-land", "ln-stat", "split", "staged", "pre-w", "w-ok", "mma", "epi", "units", "fn-end", "body", "barrier"]
     agg = OrderedDict()
     for row in rows:
-        st, mode, layer, b0, w0, b1, w1 = row[:7]
-        a = agg.setdefault((STAGES[st], MODES[mode]), [0] * 13)
-        a[0] += 1; a[1] += b0; a[2] += w0; a[3] += b1; a[4] += w1
-        for k in range(8):
-            a[5 + k] += max(row[7 + k], 0)
+        st, mode, layer, bN, wN = row[:5]
+        raw = row[5:21]
+        a = agg.setdefault((STAGES[st], MODES[mode]), np.zeros(3 + len(order) + 2))
+        a[0] += 1; a[1] += bN; a[2] += wN
+        for k, idx in enumerate(order):
+            a[3 + k] += max(raw[idx], 0)
+        a[3 + len(order)] += raw[11]; a[4 + len(order)] += raw[12]
     print(f"{preset} K={heads} iterations={tr.iterations} decode {tr.ms_decode:.3f} ms "
           f"({tr.ms_decode / max(1, tr.iterations):.3f} ms/iter), encoder {tr.ms_encoder:.3f} ms, mel {tr.ms_mel:.3f} ms")
-    sub = ["desc", "x-load", "ln-stat", "x-loop", "x-sync", "w-ready", "mma", "epi"]
-    print(f"{'stage':<12}{'mode':<5}{'n':>3}{'body0':>7}{'wait0':>7}{'bodyN':>7}{'waitN':>7}{'total':>8}"
-          + "".join(f"{x:>8}" for x in sub) + "   (us; sub-phases = offsets from stage begin, CTA 0)")
+    print(f"{'stage':<12}{'mode':<5}{'n':>3}" + "".join(f"{x:>8}" for x in names) + f"{'bodyN':>8}{'waitN':>8}  w@begin w@wait"
+          "   (us; CTA 0 offsets from stage begin; bodyN/waitN = last CTA)")
     tot = 0.0
     for (st, mode), a in agg.items():
         cnt = a[0]
-        t = (a[1] + a[2]) / 1e3
-        tot += t
-        print(f"{st:<12}{mode:<5}{cnt:>3}{a[1] / cnt / 1e3:>7.2f}{a[2] / cnt / 1e3:>7.2f}{a[3] / cnt / 1e3:>7.2f}"
-              f"{a[4] / cnt / 1e3:>7.2f}{t:>8.1f}" + "".join(f"{a[5 + k] / cnt / 1e3:>8.2f}" for k in range(8)))
+        tot += a[3 + len(order) - 1] / 1e3
+        print(f"{st:<12}{mode:<5}{int(cnt):>3}" + "".join(f"{a[3 + k] / cnt / 1e3:>8.2f}" for k in range(len(order)))
+              + f"{a[1] / cnt / 1e3:>8.2f}{a[2] / cnt / 1e3:>8.2f}  {a[3 + len(order)] / cnt / 1e3:>7.2f} {a[4 + len(order)] / cnt / 1e3:>6.2f}")
     print(f"sum over stages of the last iteration (CTA 0): {tot / 1e3:.3f} ms")
     model.close()
 

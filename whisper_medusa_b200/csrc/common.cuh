@@ -27,19 +27,20 @@ struct ChunkDesc {
 struct alignas(16) CtaStage {
   int stage, mode, layer;   // StageId, pass mode, decoder layer
   int epi;                  // GEMM stages: epilogue kind
-  const float* X;           // activation rows (fp32), already offset by x_row0 and the k segment
-  const float* bias;        // [N] or null
-  const float* ln_g;        // LayerNorm of the activations (null: plain)
-  const float* ln_b;
-  float* out;
-  __half* kc;               // EPI_QKV: self K/V cache of the layer
-  __half* vc;
-  const void* pf[2];        // vectors worth pulling into L2 for the NEXT LayerNorm stage (its ln_g, ln_b)
+  int ln;                   // 1: the activations go through LayerNorm (its vectors arrive via nx_g/nx_b of the previous record)
   int x_ld;                 // row stride of X in floats
   int x_rows_fixed;         // 0: the pass's T rows
   int n_begin, n_rows;      // W rows of this CTA
   int N, ldo, out_row0;
   int segs, seg, block;     // K split (FC2): segs > 1
+  int pf_bias_lines;        // 128-byte lines of pf_bias
+  const float* X;           // activation rows (fp32), already offset by x_row0 and the k segment
+  const float* bias;        // [N] or null
+  float* out;
+  const float* nx_g;        // LayerNorm vectors of the NEXT instruction (null: it has none)
+  const float* nx_b;
+  const float* pf_bias;     // this CTA's bias slice of the next GEMM stage (L2 prefetch)
+  int pad_[4];
 };
 static_assert(sizeof(CtaStage) == 128, "CtaStage must be one 128-byte line");
 

@@ -330,7 +330,7 @@ __device__ __noinline__ void stage_gemm(const GemmDesc& g, int cta, int ncta, un
 // Row t sees keys 0 .. base + t.  K/V rows come straight from L2 (the cache is small and hot).
 // -----------------------------------------------------------------------------------------
 #define WM_SA_MAXR 4
-__host__ __device__ inline size_t self_attn_smem_bytes() {
+__host__ __device__ constexpr size_t self_attn_smem_bytes() {
   return (size_t)(WM_SA_MAXR * 64 + WM_SA_MAXR * WM_MAX_POS + 2 * WM_SA_MAXR + 60 * 64) * sizeof(float);
 }
 __device__ __forceinline__ float dot64_h(const float* q, const uint4* kp) {
@@ -438,7 +438,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
 // -----------------------------------------------------------------------------------------
 #define WM_CH_MAX 216   // keys per chunk (S = 1500 over >= 7 chunks)
 #define WM_CH_PAD 224   // rounded up to the MMA k-step (16 keys)
-__host__ __device__ inline size_t cross_attn_smem_bytes() {
+__host__ __device__ constexpr size_t cross_attn_smem_bytes() {
   return (size_t)2 * WM_CH_PAD * 72 * sizeof(__half) + (size_t)WM_MAX_T * WM_CH_PAD * sizeof(float) +
          (size_t)2 * 16 * 72 * sizeof(__half) + (size_t)2 * WM_MAX_T * sizeof(float);
 }
@@ -1120,7 +1120,14 @@ void dec_build_program(int n_layers, int has_block, std::vector<int>& flat, int 
   off[3] = (int)flat.size() / 3;
 }
 
-size_t dec_ring_smem_bytes(int d) { return ring_smem_bytes(d); }
+size_t dec_ring_smem_bytes(int d) {
+  switch (d) {
+#define WM_CASE(DD) case DD: return RingGeom<DD>::TOTAL;
+    WM_RING_WIDTHS(WM_CASE)
+#undef WM_CASE
+    default: return 0;   // width not instantiated: dec_configure / the launch report the error
+  }
+}
 
 // Per-CTA chunk schedule of the ring producer, in exactly the order stage_gemm_ring consumes:
 // for every GEMM stage of the program with work for the CTA (gemm_work): for unit (16 rows).
@@ -1164,28 +1171,42 @@ void dec_build_stage_table(const DecModel& hm, int ncta, std::vector<CtaStage>& 
   const PassGeom dyn{-1, 0};   // T = -1: "the rows of the pass" (resolved on the device)
   for (int ip = 0; ip < n; ++ip) {
     const int stage = flat[ip * 3], mode = flat[ip * 3 + 1], layer = flat[ip * 3 + 2];
-    // LayerNorm vectors of the next LN-fed GEMM stage in program order (L2 prefetch hint)
-    const void* pf0 = nullptr; const void* pf1 = nullptr;
-    for (int jp = ip + 1; jp < n && jp < ip + 6; ++jp) {
-      if (!is_gemm_stage(flat[jp * 3])) continue;
-      const GemmDesc gn = make_gemm_desc(&hm, flat[jp * 3], flat[jp * 3 + 1], flat[jp * 3 + 2], &dyn);
-      if (gn.xsrc == XS_LN) { pf0 = gn.ln_g; pf1 = gn.ln_b; break; }
+    // LayerNorm vectors of the next instruction (bulk-copied into shared memory while this one ends) ...
+    const float* nx_g = nullptr; const float* nx_b = nullptr;
+    const bool list_end = (ip + 1 == poff[1] || ip + 1 == poff[2] || ip + 1 == poff[3]);
+    if (ip + 1 < n && is_gemm_stage(flat[(ip + 1) * 3])) {
+      const GemmDesc gn = make_gemm_desc(&hm, flat[(ip + 1) * 3], flat[(ip + 1) * 3 + 1], flat[(ip + 1) * 3 + 2], &dyn);
+      if (gn.xsrc == XS_LN) { nx_g = gn.ln_g; nx_b = gn.ln_b; }
     }
+    (void)list_end;
+    // ... and the next GEMM stage (bias prefetch)
+    int jn = -1;
+    for (int jp = ip + 1; jp < n && jp < ip + 4; ++jp)
+      if (is_gemm_stage(flat[jp * 3])) { jn = jp; break; }
     for (int cta = 0; cta < ncta; ++cta) {
       CtaStage& c = tab[(size_t)ip * ncta + cta];
       c.stage = stage; c.mode = mode; c.layer = layer;
-      c.pf[0] = pf0; c.pf[1] = pf1;
+      c.nx_g = nx_g; c.nx_b = nx_b;
+      if (jn >= 0) {
+        const GemmDesc gn = make_gemm_desc(&hm, flat[jn * 3], flat[jn * 3 + 1], flat[jn * 3 + 2], &dyn);
+        const GemmWork wn = gemm_work(gn.N, gn.K, hm.d, cta, ncta);
+        if (gn.bias && wn.n_rows > 0) {
+          const uintptr_t a0 = (uintptr_t)(gn.bias + wn.n_begin) & ~(uintptr_t)127;
+          const uintptr_t a1 = (uintptr_t)(gn.bias + wn.n_begin + wn.n_rows);
+          c.pf_bias = reinterpret_cast<const float*>(a0);
+          c.pf_bias_lines = (int)std::min<uintptr_t>(32, (a1 - a0 + 127) / 128);
+        }
+      }
       if (!is_gemm_stage(stage)) continue;
       const GemmDesc g = make_gemm_desc(&hm, stage, mode, layer, &dyn);
       const GemmWork wk = gemm_work(g.N, g.K, hm.d, cta, ncta);
       c.epi = g.epi;
+      c.ln = (g.xsrc == XS_LN) ? 1 : 0;
       c.X = g.X + (size_t)g.x_row0 * g.K + (size_t)wk.seg * hm.d;
       c.x_ld = g.K;
       c.x_rows_fixed = g.x_rows < 0 ? 0 : g.x_rows;
       c.bias = g.bias;
-      c.ln_g = (g.xsrc == XS_LN) ? g.ln_g : nullptr;
-      c.ln_b = (g.xsrc == XS_LN) ? g.ln_b : nullptr;
-      c.out = g.out; c.kc = g.kc; c.vc = g.vc;
+      c.out = g.out;
       c.n_begin = wk.n_begin; c.n_rows = wk.n_rows;
       c.N = g.N; c.ldo = g.ldo; c.out_row0 = g.out_row0;
       c.segs = wk.segs; c.seg = wk.seg; c.block = wk.block;
@@ -1195,7 +1216,13 @@ void dec_build_stage_table(const DecModel& hm, int ncta, std::vector<CtaStage>& 
 
 cudaError_t dec_launch_iteration_ring(const DecModel* dm, const DecHostInfo& hi, bool profile, cudaStream_t s) {
   void* args[] = {(void*)&dm};
-  void* fn = profile ? (void*)dec_iteration_ring_kernel<true> : (void*)dec_iteration_ring_kernel<false>;
+  void* fn = nullptr;
+  switch (hi.d) {
+#define WM_CASE(DD) case DD: fn = profile ? (void*)dec_iteration_ring_kernel<DD, true> : (void*)dec_iteration_ring_kernel<DD, false>; break;
+    WM_RING_WIDTHS(WM_CASE)
+#undef WM_CASE
+    default: return cudaErrorInvalidValue;
+  }
   return cudaLaunchCooperativeKernel(fn, dim3(hi.n_sm), dim3(WM_RING_THREADS), args, hi.smem_ring, s);
 }
 
@@ -1208,14 +1235,22 @@ size_t dec_smem_bytes(int d, int ffn) {
   return s;
 }
 
-cudaError_t dec_configure(size_t smem, size_t smem_ring) {
+cudaError_t dec_configure(int d, size_t smem, size_t smem_ring) {
   cudaError_t e = cudaFuncSetAttribute(dec_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(dec_iteration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(dec_iteration_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dec_iteration_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring);
+  if (smem_ring == 0) return cudaSuccess;   // decoder width without a ring instantiation: persistent mode refuses to run
+  switch (d) {
+#define WM_CASE(DD)                                                                                                          \
+  case DD:                                                                                                                   \
+    e = cudaFuncSetAttribute(dec_iteration_ring_kernel<DD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring); \
+    if (e != cudaSuccess) return e;                                                                                          \
+    return cudaFuncSetAttribute(dec_iteration_ring_kernel<DD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring);
+    WM_RING_WIDTHS(WM_CASE)
+#undef WM_CASE
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 static int stage_grid(int stage, int T, int n_sm, int H, int K) {

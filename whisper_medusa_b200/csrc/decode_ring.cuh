@@ -15,9 +15,16 @@
 // chasing on the device), waits on `empty[slot]`, arms `full[slot]` with the byte count and lets
 // lanes 0..nrows-1 issue one bulk copy per weight row.
 //
-// Control data never waits on L2 after a barrier (every grid barrier invalidates L1): the model
-// description lives in a shared-memory copy, the pass geometry in registers, and the next stage
-// instruction is loaded before the barrier it follows.
+// Everything on the critical path of a stage is either resident or asynchronous:
+//   * the kernel is a template of the model width D: strides, slice counts and every shared-memory
+//     offset are immediates (no integer divisions, few live registers -- with a 227 KB carve-out
+//     only ~27 KB of L1 remain, so a register spill is an L2 round trip);
+//   * the stage record of this CTA (row range, pointers, epilogue; built by the host) is prefetched
+//     into shared memory while the previous stage runs;
+//   * activations arrive by bulk copy and are split in place (see below); the LayerNorm vectors of
+//     the next stage are bulk-copied during the barrier that precedes it; bias vectors are pulled
+//     into L2 one stage ahead and read while the MMAs run.  (A plain global load that is still in
+//     flight at a bar.sync stalls the barrier: no long-latency ld may precede one.)
 //
 // Stages with K > d (FC2) are split over CTAs along K as well: CTA = (row block, k segment); the
 // segment partials go to a global scratch and the CTA that arrives last for a row block folds
@@ -66,7 +73,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __host__ __device__ __forceinline__ bool is_gemm_stage(int st) {
   return st == ST_QKV || st == ST_OPROJ || st == ST_CROSS_Q || st == ST_CROSS_O || st == ST_FC1 || st == ST_FC2 ||
@@ -120,45 +127,64 @@ __host__ __device__ __forceinline__ GemmWork gemm_work(int N, int K, int d, int 
   return w;
 }
 
-struct RingCtx {
-  unsigned char* ring;     // WM_RING_G slots
-  uint64_t* full;          // WM_RING_G mbarriers (producer -> compute)
-  uint64_t* empty;         // WM_RING_G mbarriers (compute -> producer)
-  int row_stride;          // bytes
-  int slot_bytes;
-  int d;
-  int cta, ncta;
-  unsigned int consumed;   // chunks consumed so far in this launch (uniform across the compute warps)
-  uint64_t* xbar;          // mbarrier of the activation-row bulk copies
-  unsigned int xphase;     // its parity
+// ---------------------------------------------------------------------------------------------
+// compile-time geometry of the kernel for model width D
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
+__host__ __device__ constexpr size_t round128(size_t a) { return (a + 127) / 128 * 128; }
+__host__ __device__ constexpr int ring_nks(int d) { return (d % 256 == 0) ? 8 : (d % 128 == 0) ? 4 : (d % 64 == 0) ? 2 : 1; }
+
+#define WM_XS_PADB 16   // bytes of X-row padding: stride = 16 (mod 128) => conflict-free LDS.128 / STS.128
+
+template <int D>
+struct RingGeom {
+  static_assert(D % 32 == 0 && D <= 1280, "decoder width must be a multiple of 32, at most 1280");
+  static constexpr int ROW_STRIDE = D * 2 + 64;       // ring row stride, bytes
+  static constexpr int SLOT_BYTES = 16 * ROW_STRIDE;
+  static constexpr int XS = D * 4 + WM_XS_PADB;       // activation row stride, bytes
+  static constexpr int NKS = ring_nks(D);             // k-slices per chunk (one MMA warp each)
+  static constexpr int KS = D / NKS;
+  static_assert(KS % 32 == 0, "k-slice must be a multiple of the 32-column MMA step");
+  static constexpr int NV4 = D / 4;                   // float4 per activation row
+  static constexpr int NV = (D + 127) / 128;          // float4 per lane of a row-per-warp pass
+  // shared-memory map
+  static constexpr size_t SCRATCH_OFF = (size_t)WM_RING_G * SLOT_BYTES;
+  static constexpr size_t SCRATCH = round128(cmax(cmax((size_t)16 * XS, cross_attn_smem_bytes()), self_attn_smem_bytes()));
+  static constexpr size_t PARTIAL_OFF = SCRATCH_OFF + SCRATCH;
+  static constexpr size_t PARTIAL = round128(cmax((size_t)8 * 256 * sizeof(float), (size_t)2 * D * sizeof(float)));
+  static constexpr size_t MODEL_OFF = PARTIAL_OFF + PARTIAL;
+  static constexpr size_t MODEL = round128(sizeof(DecModel));
+  static constexpr size_t BAR_OFF = MODEL_OFF + MODEL;
+  static constexpr size_t TOTAL = BAR_OFF + 128;
 };
 
 // ---------------------------------------------------------------------------------------------
 // producer warp: stream the chunk table through the ring
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void ring_producer(unsigned char* ring, uint64_t* full, uint64_t* empty, int row_stride, int slot_bytes,
-                                           int d, const ChunkDesc* __restrict__ tab, int first, int last) {
+template <int D>
+__device__ __noinline__ void ring_producer(unsigned char* ring, uint64_t* full, uint64_t* empty,
+                                           const ChunkDesc* __restrict__ tab, int first, int last) {
+  using G = RingGeom<D>;
   const int lane = threadIdx.x & 31;
   if (first >= last) return;
   ChunkDesc nxt = tab[first];
+  int slot = 0;
+  unsigned int par = 1;   // parity to wait for on `empty` (fresh barrier: the "previous" phase counts as complete)
   for (int c = first; c < last; ++c) {
-    const unsigned int k = (unsigned int)(c - first);
-    const int slot = k % WM_RING_G;
-    const unsigned int round = k / WM_RING_G;
     const ChunkDesc dsc = nxt;
     if (c + 1 < last) nxt = tab[c + 1];                 // next descriptor is in flight while we wait
     if (lane == 0) {
-      while (!mbar_try_wait(empty + slot, (round & 1) ^ 1)) { }
+      while (!mbar_try_wait(empty + slot, par)) { }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the slot vs async writes
-      mbar_expect_tx(full + slot, (uint32_t)(dsc.nrows * d * 2));
+      mbar_expect_tx(full + slot, (uint32_t)(dsc.nrows * D * 2));
     }
     __syncwarp();
     if (lane < dsc.nrows) {
-      bulk_g2s(ring + (size_t)slot * slot_bytes + (size_t)lane * row_stride,
-               reinterpret_cast<const unsigned char*>(dsc.src) + (size_t)lane * dsc.row_bytes, (uint32_t)(d * 2),
-               full + slot);
+      bulk_g2s(ring + (size_t)slot * G::SLOT_BYTES + (size_t)lane * G::ROW_STRIDE,
+               reinterpret_cast<const unsigned char*>(dsc.src) + (size_t)lane * dsc.row_bytes, (uint32_t)(D * 2), full + slot);
     }
     __syncwarp();
+    if (++slot == WM_RING_G) { slot = 0; par ^= 1u; }
   }
 }
 
@@ -172,11 +198,9 @@ __device__ __noinline__ void ring_producer(unsigned char* ring, uint64_t* full, 
 // every 8-byte pair of floats (x[k], x[k+1]) becomes { half2 hi(k,k+1), half2 lo(k,k+1) }, so one
 // LDS.128 of the MMA loop fetches the hi AND lo A-fragment registers of two k-pairs.
 // LayerNorm stages: warp-per-row statistics out of shared memory, then thread-per-column
-// normalisation with that column's gamma/beta held in registers (loaded before the wait on X).
+// normalisation with gamma/beta read from the shared parameter buffer.
 // Rows >= T keep stale bits: MMA rows are independent and rows >= T are never stored.
 // ---------------------------------------------------------------------------------------------
-#define WM_XS_PADB 16   // bytes of row padding: stride = 16 (mod 128) => conflict-free LDS.128 / STS.128
-
 __device__ __forceinline__ uint4 split_hilo4(float4 y) {
   // packed conversions: hi = rn(x), lo = rn(x - hi)
   const __half2 a = __floats2half2_rn(y.x, y.y), b = __floats2half2_rn(y.z, y.w);
@@ -193,98 +217,99 @@ __device__ __forceinline__ float xbuf_value(const unsigned char* xb, int xs, int
   const __half* p = reinterpret_cast<const __half*>(xb + (size_t)r * xs + (size_t)(n >> 1) * 8) + (n & 1);
   return __half2float(p[0]) + __half2float(p[2]);
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-#define WM_LN_MAXV 10   // float4 per lane: d <= 1280 (every Whisper size)
+// per-thread state of the compute warps that survives across stages (uniform over the CTA)
+struct RingState {
+  int slot;            // ring slot of the next chunk to consume
+  unsigned int par;    // its `full` parity
+  unsigned int xpar;   // parity of the activation-copy barrier
+  unsigned int ppar;   // parity of the LayerNorm-vector barrier
+};
 
 // ---------------------------------------------------------------------------------------------
 // GEMM stage fed from the ring (compute warps).  `sd` = this CTA's resolved record (shared memory).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, const CtaStage* sd, int Tpass, int base,
-                                                unsigned char* xb, float* partial, unsigned long long* pr) {
+template <int D>
+__device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* smem, const DecModel* m, const CtaStage* sd,
+                                                int Tpass, int base, unsigned long long* pr) {
+  using G = RingGeom<D>;
   __shared__ int s_last;
   __shared__ float2 s_stat[WM_MAX_T];
   const int n_rows = sd->n_rows;
-  if (n_rows == 0) return;   // the chunk table has no entry for such stages either
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = WM_DEC_THREADS >> 5;
+  unsigned char* const xb = smem + G::SCRATCH_OFF;
+  float* const partial = reinterpret_cast<float*>(smem + G::PARTIAL_OFF);
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem + G::BAR_OFF);
+  uint64_t* const empty = full + WM_RING_G;
+  uint64_t* const xbar = empty + WM_RING_G;
+  uint64_t* const pbar = xbar + 1;
+  if (n_rows == 0) {
+    // no rows for this CTA (narrow models; the chunk table has no entry either) -- but the LayerNorm vectors
+    // were sent to every CTA: consume that phase
+    if (sd->ln) { while (!mbar_try_wait(pbar, rs.ppar)) { } rs.ppar ^= 1u; }
+    return;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int nwarps = WM_DEC_THREADS >> 5;
   const int gq = lane >> 2, tq = lane & 3;
-  const int d = rc.d;
-  const int XS = d * 4 + WM_XS_PADB;
   const int T = sd->x_rows_fixed ? sd->x_rows_fixed : Tpass;
-  const bool ln = sd->ln_g != nullptr;
-  const int nv4 = d >> 2;
+  const bool ln = sd->ln != 0;
 
-  if (pr) pr[7] = global_timer_ns();
+  if (pr) {
+    pr[7] = global_timer_ns();
+    pr[11] = mbar_try_wait(full + rs.slot, rs.par) ? 1000ull : 0ull;   // weights already here?
+  }
   // ---- X rows: global (L2) -> shared, one bulk copy per row ----
   if (warp == 0) {
     if (lane == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of the buffer vs async writes
-      mbar_expect_tx(rc.xbar, (uint32_t)(T * d * 4));
+      mbar_expect_tx(xbar, (uint32_t)(T * D * 4));
     }
     __syncwarp();
-    if (lane < T) bulk_g2s(xb + (size_t)lane * XS, sd->X + (size_t)lane * sd->x_ld, (uint32_t)(d * 4), rc.xbar);
+    if (lane < T) bulk_g2s(xb + (size_t)lane * G::XS, sd->X + (size_t)lane * sd->x_ld, (uint32_t)(D * 4), xbar);
+  } else if (warp == 1) {
+    // this CTA's bias slice of the NEXT GEMM stage -> L2 (biases are cold: 2 GB of weights pass through L2 per iteration)
+    if (lane < sd->pf_bias_lines) prefetch_l2(reinterpret_cast<const unsigned char*>(sd->pf_bias) + (size_t)lane * 128);
   }
-  // this thread's LayerNorm column (in flight while X arrives)
-  float4 gg = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ln && tid < nv4) {
-    gg = reinterpret_cast<const float4*>(sd->ln_g)[tid];
-    bb = reinterpret_cast<const float4*>(sd->ln_b)[tid];
-  }
-  const int units = (n_rows + 15) >> 4;
-  const bool ksplit = sd->segs > 1;
-  const int epi = sd->epi;
-  const int n_begin = sd->n_begin;
   // output element owned by this thread in the fold below
-  const int e_ = tid >> 5, ln_ = tid & 31;
+  const int e_ = tid >> 5;
   const int j_ = (e_ >> 2) & 1, i_ = e_ & 3;
-  const int token = (ln_ >> 2) + ((i_ >= 2) ? 8 : 0);
-  const int rloc = j_ * 8 + 2 * (ln_ & 3) + (i_ & 1);
+  const int token = gq + ((i_ >= 2) ? 8 : 0);
+  const int rloc = j_ * 8 + 2 * tq + (i_ & 1);
   const bool mine = tid < 256 && token < T;
-  // residual epilogue: fetch the old value while X arrives / the MMAs run (single-unit stages only)
-  float old = 0.f;
-  const bool pre_old = (epi == EPI_RESID) && !ksplit && units == 1 && mine && rloc < n_rows;
-  if (pre_old) old = ldcg_f(&sd->out[(size_t)token * sd->ldo + n_begin + rloc]);
-  float bias_v = 0.f;        // bias of this thread's row in unit 0 (later units reload)
-  {
-    const float* bias = sd->bias;
-    if (mine && rloc < n_rows && bias && !ksplit) bias_v = bias[n_begin + rloc];
-  }
-  // pull the next LayerNorm stage's gamma / beta into L2 (they are cold: 2 GB of weights pass through L2 per iteration)
-  if (sd->pf[0] && tid >= 256 && tid < 256 + 2 * ((d * 4 + 127) >> 7)) {
-    const int i = tid - 256, half = (d * 4 + 127) >> 7;
-    const unsigned char* p = reinterpret_cast<const unsigned char*>(i < half ? sd->pf[0] : sd->pf[1]);
-    prefetch_l2(p + (size_t)(i < half ? i : i - half) * 128);
-  }
 
-  while (!mbar_try_wait(rc.xbar, rc.xphase)) { }
-  rc.xphase ^= 1u;
+  while (!mbar_try_wait(xbar, rs.xpar)) { }
+  rs.xpar ^= 1u;
   if (pr) pr[8] = global_timer_ns();
   if (ln) {
     // statistics: one warp per row, lane l sums float4 columns l, l+32, ... (two passes over shared memory)
-    const int nv = d >> 7;
     for (int r = warp; r < T; r += nwarps) {
-      const float4* x4 = reinterpret_cast<const float4*>(xb + (size_t)r * XS) + lane;
+      const float4* x4 = reinterpret_cast<const float4*>(xb + (size_t)r * G::XS) + lane;
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < WM_LN_MAXV; ++i)
-        if (i < nv) { const float4 v = x4[i * 32]; s += (v.x + v.y) + (v.z + v.w); }
-      const float mean = warp_sum(s) / (float)d;
+      for (int i = 0; i < G::NV; ++i)
+        if (i * 32 + lane < G::NV4) { const float4 v = x4[i * 32]; s += (v.x + v.y) + (v.z + v.w); }
+      const float mean = warp_sum(s) / (float)D;
       float q = 0.f;
 #pragma unroll
-      for (int i = 0; i < WM_LN_MAXV; ++i)
-        if (i < nv) {
+      for (int i = 0; i < G::NV; ++i)
+        if (i * 32 + lane < G::NV4) {
           const float4 v = x4[i * 32];
           const float a = v.x - mean, b = v.y - mean, c = v.z - mean, e = v.w - mean;
           q += (a * a + b * b) + (c * c + e * e);
         }
-      const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+      const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-5f);
       if (lane == 0) s_stat[r] = make_float2(mean, rstd);
     }
+    // gamma / beta were bulk-copied into the (idle) partial buffer during the preceding barrier
+    while (!mbar_try_wait(pbar, rs.ppar)) { }
+    rs.ppar ^= 1u;
     cta_sync();
     if (pr) pr[9] = global_timer_ns();
-    if (tid < nv4) {
+    if (tid < G::NV4) {
+      const float4 gg = reinterpret_cast<const float4*>(partial)[tid];
+      const float4 bb = reinterpret_cast<const float4*>(partial)[G::NV4 + tid];
       for (int r = 0; r < T; ++r) {
-        uint4* p = reinterpret_cast<uint4*>(xb + (size_t)r * XS) + tid;
+        uint4* p = reinterpret_cast<uint4*>(xb + (size_t)r * G::XS) + tid;
         const float4 v = *reinterpret_cast<const float4*>(p);
         const float2 st = s_stat[r];
         float4 y;
@@ -298,42 +323,42 @@ __device__ __forceinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, 
   } else {
     // flat over the buffer (the 16-byte row pad is converted along: no index arithmetic)
     uint4* p = reinterpret_cast<uint4*>(xb);
-    const int n16 = T * (XS >> 4);
+    const int n16 = T * (G::XS >> 4);
     for (int idx = tid; idx < n16; idx += WM_DEC_THREADS) p[idx] = split_hilo4(*reinterpret_cast<const float4*>(p + idx));
   }
   if (pr) pr[10] = global_timer_ns();
   cta_sync();
   if (pr) pr[3] = global_timer_ns();
-  int nks = 8;               // k-slices per chunk: one warp each, both n8 tiles of the chunk
-  while ((d / nks) % 32 != 0) nks >>= 1;
-  const int KS = d / nks;
-  const int rs_h = rc.row_stride / 2;   // ring row stride in halfs
+  const int units = (n_rows + 15) >> 4;
+  const bool ksplit = sd->segs > 1;
+  const int epi = sd->epi;
+  const int n_begin = sd->n_begin;
   for (int u = 0; u < units; ++u) {
-    const unsigned int c = rc.consumed;
-    const int slot = c % WM_RING_G;
     const int nvalid = min(16, n_rows - u * 16);
-    // this thread's bias for the unit: in flight while the MMAs run
-    if (u > 0) {
+    // this thread's bias and (residual epilogue) old value: L2 hits that complete while the MMAs run
+    float bias_v = 0.f, old = 0.f;
+    if (mine && rloc < nvalid && !ksplit) {
       const float* bias = sd->bias;
-      bias_v = 0.f;
-      if (mine && rloc < nvalid && bias && !ksplit) bias_v = bias[n_begin + u * 16 + rloc];
+      if (bias) bias_v = bias[n_begin + u * 16 + rloc];
+      if (epi == EPI_RESID) old = ldcg_f(&sd->out[(size_t)token * sd->ldo + n_begin + u * 16 + rloc]);
     }
-    while (!mbar_try_wait(rc.full + slot, (c / WM_RING_G) & 1)) { }
+    if (pr && u == 0) { pr[12] = mbar_try_wait(full + rs.slot, rs.par) ? 1000ull : 0ull; pr[13] = global_timer_ns(); }
+    while (!mbar_try_wait(full + rs.slot, rs.par)) { }
     if (pr && u == 0) pr[4] = global_timer_ns();
-    if (warp < nks) {
-      const __half* sl = reinterpret_cast<const __half*>(rc.ring + (size_t)slot * rc.slot_bytes);
+    if (warp < G::NKS) {
+      const __half* sl = reinterpret_cast<const __half*>(smem + (size_t)rs.slot * G::SLOT_BYTES);
       const bool v0 = gq < nvalid, v1 = (gq + 8) < nvalid;
-      const __half* w0p = sl + (size_t)gq * rs_h + warp * KS + 8 * tq;
-      const __half* w1p = sl + (size_t)(gq + 8) * rs_h + warp * KS + 8 * tq;
-      const unsigned char* x0 = xb + (size_t)gq * XS + (size_t)(warp * KS + 8 * tq) * 4;
-      const unsigned char* x1 = x0 + (size_t)8 * XS;
+      const __half* w0p = sl + (size_t)gq * (G::ROW_STRIDE / 2) + warp * G::KS + 8 * tq;
+      const __half* w1p = w0p + (size_t)8 * (G::ROW_STRIDE / 2);
+      const unsigned char* x0 = xb + (size_t)gq * G::XS + (size_t)(warp * G::KS + 8 * tq) * 4;
+      const unsigned char* x1 = x0 + (size_t)8 * G::XS;
       const bool t1 = (gq + 8) < T;   // token rows 8..15 contribute nothing when T <= 8 + gq
       // four independent accumulator chains: (n8 tile 0 / 1) x (hi / lo part of X)
       float c0h[4] = {0.f, 0.f, 0.f, 0.f}, c0l[4] = {0.f, 0.f, 0.f, 0.f};
       float c1h[4] = {0.f, 0.f, 0.f, 0.f}, c1l[4] = {0.f, 0.f, 0.f, 0.f};
       const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll 5
-      for (int kk = 0; kk < KS; kk += 32) {
+#pragma unroll
+      for (int kk = 0; kk < G::KS; kk += 32) {
         const uint4 wa = v0 ? *reinterpret_cast<const uint4*>(w0p + kk) : z;
         const uint4 wb = v1 ? *reinterpret_cast<const uint4*>(w1p + kk) : z;
         // {hi(k,k+1), lo(k,k+1), hi(k+2,k+3), lo(k+2,k+3)} for k = kk + 8 tq and k + 4
@@ -352,17 +377,18 @@ __device__ __forceinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, 
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        partial[(size_t)warp * 256 + e * 32 + lane] = c0h[e] + c0l[e];
-        partial[(size_t)warp * 256 + (4 + e) * 32 + lane] = c1h[e] + c1l[e];
+        partial[warp * 256 + e * 32 + lane] = c0h[e] + c0l[e];
+        partial[warp * 256 + (4 + e) * 32 + lane] = c1h[e] + c1l[e];
       }
     }
     cta_sync();   // partials visible; every read of the slot is done
     if (pr && u == 0) pr[5] = global_timer_ns();
-    rc.consumed = c + 1;
-    if (tid == 0) mbar_arrive(rc.empty + slot);   // hand the slot back to the producer
+    if (tid == 0) mbar_arrive(empty + rs.slot);   // hand the slot back to the producer
+    if (++rs.slot == WM_RING_G) { rs.slot = 0; rs.par ^= 1u; }
     if (mine && rloc < nvalid) {
       float s = 0.f;
-      for (int ks = 0; ks < nks; ++ks) s += partial[(size_t)ks * 256 + tid];
+#pragma unroll
+      for (int ks = 0; ks < G::NKS; ++ks) s += partial[ks * 256 + tid];
       const int row = n_begin + u * 16 + rloc;
       float* out = sd->out;
       const int ldo = sd->ldo;
@@ -370,34 +396,34 @@ __device__ __forceinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, 
       if (ksplit) {
         m->gemm_part[((size_t)sd->seg * 16 + token) * sd->N + row] = s;
       } else if (epi == EPI_RESID) {
-        float* o = out + (size_t)token * ldo + row;
-        *o = (pre_old ? old : ldcg_f(o)) + (s + bias_v);
+        out[(size_t)token * ldo + row] = old + (s + bias_v);
       } else if (epi == EPI_STORE || epi == EPI_LOGITS) {
         out[(size_t)token * ldo + row] = s + bias_v;
       } else if (epi == EPI_GELU) {
         out[(size_t)token * ldo + row] = gelu_erf(s + bias_v);
       } else if (epi == EPI_QKV) {
         const float v = s + bias_v;
-        if (row < d) out[(size_t)token * ldo + row] = v;
-        else if (row < 2 * d) sd->kc[(size_t)(base + token) * d + (row - d)] = __float2half_rn(v);
-        else sd->vc[(size_t)(base + token) * d + (row - 2 * d)] = __float2half_rn(v);
+        const DecLayer& L = m->layers[sd->layer];
+        if (row < D) out[(size_t)token * ldo + row] = v;
+        else if (row < 2 * D) L.self_k[(size_t)(base + token) * D + (row - D)] = __float2half_rn(v);
+        else L.self_v[(size_t)(base + token) * D + (row - 2 * D)] = __float2half_rn(v);
       } else if (epi == EPI_HEADS_A) {
         // head `row / d` on the newest token's hidden state: x + SiLU(W x + b)  (medusa ResBlock)
-        const int head = row / d, n = row - head * d;
-        out[(size_t)(sd->out_row0 + head) * ldo + n] = xbuf_value(xb, XS, 0, n) + silu(s + bias_v);
+        const int head = row / D, n = row - head * D;
+        out[(size_t)(sd->out_row0 + head) * ldo + n] = xbuf_value(xb, G::XS, 0, n) + silu(s + bias_v);
       } else {   // EPI_HEAD_B
-        out[(size_t)token * ldo + row] = xbuf_value(xb, XS, token, row) + silu(s + bias_v);
+        out[(size_t)token * ldo + row] = xbuf_value(xb, G::XS, token, row) + silu(s + bias_v);
       }
     }
     cta_sync();   // partial buffer reusable
     if (pr && u == 0) pr[6] = global_timer_ns();
   }
+  if (pr) pr[14] = global_timer_ns();
   if (ksplit) {
     // the last of the `segs` CTAs of this row block folds the segment partials, always in segment order
     const int segs = sd->segs, block = sd->block, N = sd->N;
-    cta_sync();
     if (tid == 0) {
-      const unsigned int prev = atom_add_release(&m->gemm_cnt[block], 1u);
+      const unsigned int prev = atom_add_release(&m->gemm_cnt[block], 1u);   // (the unit loop ended with a cta_sync)
       s_last = (prev == (unsigned int)(segs - 1)) ? 1 : 0;
       if (s_last) m->gemm_cnt[block] = 0u;
     }
@@ -406,57 +432,40 @@ __device__ __forceinline__ void stage_gemm_ring(RingCtx& rc, const DecModel* m, 
       const float* bias = sd->bias;
       float* out = sd->out;
       const int ldo = sd->ldo;
-      for (int idx = tid; idx < T * n_rows; idx += WM_DEC_THREADS) {
-        const int t = idx / n_rows, row = n_begin + (idx - t * n_rows);
-        float s = 0.f;
-        for (int sg = 0; sg < segs; ++sg) s += __ldcg(m->gemm_part + ((size_t)sg * 16 + t) * N + row);
-        // K-split stages are residual GEMMs (FC2)
-        float* o = out + (size_t)t * ldo + row;
-        *o = ldcg_f(o) + (s + (bias ? bias[row] : 0.f));
+      // warp per token row, lanes over the rows of W; K-split stages are residual GEMMs (FC2)
+      for (int t = warp; t < T; t += nwarps) {
+        for (int r = lane; r < n_rows; r += 32) {
+          const int row = n_begin + r;
+          float s = 0.f;
+          for (int sg = 0; sg < segs; ++sg) s += __ldcg(m->gemm_part + ((size_t)sg * 16 + t) * N + row);
+          float* o = out + (size_t)t * ldo + row;
+          *o = ldcg_f(o) + (s + (bias ? bias[row] : 0.f));
+        }
       }
     }
   }
 }
 
-__host__ __device__ inline size_t ring_scratch_bytes(int d) {
-  size_t scratch = (size_t)16 * (d * 4 + WM_XS_PADB);
-  if (scratch < cross_attn_smem_bytes()) scratch = cross_attn_smem_bytes();
-  if (scratch < self_attn_smem_bytes()) scratch = self_attn_smem_bytes();
-  return (scratch + 127) / 128 * 128;
-}
-__host__ __device__ inline size_t ring_model_bytes() { return (sizeof(DecModel) + 127) / 128 * 128; }
-__host__ __device__ inline size_t ring_smem_bytes(int d) {
-  return (size_t)WM_RING_G * 16 * (d * 2 + 64) + ring_scratch_bytes(d) + (size_t)8 * 256 * sizeof(float) + ring_model_bytes() + 128;
-}
-
-template <bool PROF>
+template <int D, bool PROF>
 __global__ void __launch_bounds__(WM_RING_THREADS, 1)
 dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
+  using G = RingGeom<D>;
   extern __shared__ __align__(128) unsigned char smem[];
   const DecState* st = gm->st;
   if (st->done) return;
   const int need_a = st->need_a;
   const int L0 = st->L, kv0 = st->kv_len;
-  const int d = gm->d;
   const int cta = blockIdx.x, ncta = gridDim.x;
-  const int warp = threadIdx.x >> 5;
-  RingCtx rc;
-  rc.d = d;
-  rc.row_stride = d * 2 + 64;
-  rc.slot_bytes = 16 * rc.row_stride;
-  rc.ring = smem;
-  unsigned char* scratch_p = smem + (size_t)WM_RING_G * rc.slot_bytes;
-  float* partial = reinterpret_cast<float*>(scratch_p + ring_scratch_bytes(d));
-  DecModel* sm = reinterpret_cast<DecModel*>(partial + 8 * 256);   // shared-memory copy of the model description
-  rc.full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sm) + ring_model_bytes());
-  rc.empty = rc.full + WM_RING_G;
-  rc.xbar = rc.empty + WM_RING_G;
-  rc.xphase = 0u;
-  rc.cta = cta; rc.ncta = ncta;
-  rc.consumed = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  DecModel* const sm = reinterpret_cast<DecModel*>(smem + G::MODEL_OFF);   // shared-memory copy of the model description
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem + G::BAR_OFF);
+  uint64_t* const empty = full + WM_RING_G;
+  uint64_t* const xbar = empty + WM_RING_G;
+  uint64_t* const pbar = xbar + 1;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WM_RING_G; ++i) { mbar_init(rc.full + i, 1); mbar_init(rc.empty + i, 1); }
-    mbar_init(rc.xbar, 1);
+    for (int i = 0; i < WM_RING_G; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    mbar_init(xbar, 1);
+    mbar_init(pbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
@@ -471,16 +480,15 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
   if (warp == WM_DEC_THREADS / 32) {
     // ===== producer warp =====
     const int* off = m->chunk_off + cta * 4;
-    ring_producer(rc.ring, rc.full, rc.empty, rc.row_stride, rc.slot_bytes, d, m->chunk_tab, need_a ? off[0] : off[1], off[3]);
+    ring_producer<D>(smem, full, empty, m->chunk_tab, need_a ? off[0] : off[1], off[3]);
     return;
   }
 
   // ===== compute warps =====
   __shared__ CtaStage s_desc[2];   // resolved record of the running stage / the next one
   unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(&m->bar[2]);
-  unsigned int* bar = m->bar;
-  const int Kh = m->K;   // the pass geometry derives from (L0, kv0, K): the loop state only changes in the very last stage
-  const int lane = threadIdx.x & 31;
+  RingState rs;
+  rs.slot = 0; rs.par = 0u; rs.xpar = 0u; rs.ppar = 0u;
 
   const int ip_first = need_a ? m->prog_off[0] : m->prog_off[1];
   const int ip_last = m->prog_off[3];
@@ -499,22 +507,36 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
     }
     // optional per-stage timeline (CTA 0 and the last CTA): begin / end of body / end of barrier
     const bool prof = PROF && m->prof != nullptr && threadIdx.x == 0 && (cta == 0 || cta == ncta - 1);
-    unsigned long long* pr = prof ? m->prof + ((size_t)(cta == 0 ? 0 : 1) * m->prog_off[3] + ip) * 16 : nullptr;
+    unsigned long long* pr = prof ? m->prof + ((size_t)(cta == 0 ? 0 : 1) * ip_last + ip) * 16 : nullptr;
     if (prof) pr[0] = global_timer_ns();
     const int stage = sd->stage, mode = sd->mode;
-    PassGeom pgv;   // (registers: every callee that takes it is inlined)
+    // the pass geometry derives from (L0, kv0, K): the loop state only changes in the very last stage
+    PassGeom pgv;
     if (mode == MODE_A) { pgv.T = L0 - kv0; pgv.base = kv0; }
-    else if (mode == MODE_B) { pgv.T = Kh + 1; pgv.base = L0; }
+    else if (mode == MODE_B) { pgv.T = m->K + 1; pgv.base = L0; }
     else { pgv.T = 1; pgv.base = L0 - 1; }
     if (is_gemm_stage(stage)) {
-      stage_gemm_ring(rc, m, sd, pgv.T, pgv.base, scratch_p, partial, pr);
+      stage_gemm_ring<D>(rs, smem, m, sd, pgv.T, pgv.base, pr);
     } else {
-      run_stage<false>(m, stage, mode, sd->layer, cta, ncta, scratch_p, &pgv);
+      run_stage<false>(m, stage, mode, sd->layer, cta, ncta, smem + G::SCRATCH_OFF, &pgv);
     }
+    if (prof) pr[15] = global_timer_ns();
     if (fetch) reinterpret_cast<uint32_t*>(&s_desc[(ip + 1) & 1])[lane] = nxt_w;
+    // LayerNorm vectors of the next stage -> the partial buffer (idle until that stage's first MMA), in
+    // flight across the grid barrier
+    if (threadIdx.x == 0 && sd->nx_g != nullptr) {
+      float* const partial = reinterpret_cast<float*>(smem + G::PARTIAL_OFF);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(pbar, (uint32_t)(2 * D * 4));
+      bulk_g2s(partial, sd->nx_g, (uint32_t)(D * 4), pbar);
+      bulk_g2s(partial + D, sd->nx_b, (uint32_t)(D * 4), pbar);
+    }
     if (prof) pr[1] = global_timer_ns();
-    epoch = grid_barrier_step<false>(bar, epoch, ncta);
+    epoch = grid_barrier_step<false>(m->bar, epoch, ncta);
     if (prof) pr[2] = global_timer_ns();
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) m->bar[2] = epoch;
 }
+
+// model widths the ring kernel is instantiated for (Whisper tiny ... large, and the synthetic micro preset)
+#define WM_RING_WIDTHS(X) X(128) X(384) X(512) X(768) X(1024) X(1280)

@@ -293,9 +293,10 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
 
   h->hi.n_sm = h->n_sm; h->hi.H = c.n_heads; h->hi.K = c.medusa_num_heads; h->hi.n_layers = c.dec_layers;
   h->hi.has_block = m.has_block;
+  h->hi.d = (int)d;
   h->hi.smem = dec_smem_bytes((int)d, (int)f);
   h->hi.smem_ring = dec_ring_smem_bytes((int)d);
-  CK(dec_configure(h->hi.smem, h->hi.smem_ring));
+  CK(dec_configure((int)d, h->hi.smem, h->hi.smem_ring));
   {
     std::vector<int> flat;
     dec_build_program(c.dec_layers, m.has_block, flat, m.prog_off);
@@ -746,9 +747,9 @@ extern "C" int wm_set_option(wm_handle* h, const char* key, int32_t value) {
   }
   return fail(h, WM_ERR_INVALID, "unknown option " + k);
 }
-// Stage timeline of the last persistent-ring iteration (option "profile" = 1): rows of 16 int64
-// {stage, mode, layer, body_ns(cta 0), barrier_ns(cta 0), body_ns(last cta), barrier_ns(last cta),
-//  8 GEMM sub-phase offsets (ns since stage begin, CTA 0), 0}
+// Stage timeline of the last persistent-ring iteration (option "profile" = 1): rows of 24 int64
+// {stage, mode, layer, body_ns(last cta), barrier_ns(last cta), raw[16] of CTA 0, 0, 0, 0}; raw[k] is a
+// timestamp relative to the stage begin (or a flag), see dec_iteration_ring_kernel
 extern "C" int wm_get_stage_profile(wm_handle* h, int64_t* out, int32_t cap_rows, int32_t* n_rows) {
   if (!h || !out || !n_rows) return WM_ERR_INVALID;
   if (!h->prof) return fail(h, WM_ERR_STATE, "profiling is off (wm_set_option(h, \"profile\", 1))");
@@ -763,15 +764,14 @@ extern "C" int wm_get_stage_profile(wm_handle* h, int64_t* out, int32_t cap_rows
     const unsigned long long* a = &raw[(size_t)i * 16];
     const unsigned long long* b = &raw[((size_t)n + i) * 16];
     if (a[0] == 0) continue;   // stage never executed (sweep A skipped)
-    int64_t* o = out + (size_t)rows * 16;
+    int64_t* o = out + (size_t)rows * 24;
     o[0] = prog[i * 3]; o[1] = prog[i * 3 + 1]; o[2] = prog[i * 3 + 2];
-    o[3] = (int64_t)(a[1] - a[0]); o[4] = (int64_t)(a[2] - a[1]);
-    o[5] = (int64_t)(b[1] - b[0]); o[6] = (int64_t)(b[2] - b[1]);
-    // GEMM stages (CTA 0): descriptor built, X row loaded, LN statistics done, X staged + synced, staging loop
-    // left, first chunk ready, first chunk MMAs done, first chunk epilogue done
-    static const int order[8] = {7, 8, 9, 10, 3, 4, 5, 6};
-    for (int k = 0; k < 8; ++k) { const unsigned long long v = a[order[k]]; o[7 + k] = v >= a[0] ? (int64_t)(v - a[0]) : -1; }
-    o[15] = 0;
+    o[3] = (int64_t)(b[1] - b[0]); o[4] = (int64_t)(b[2] - b[1]);
+    for (int k = 0; k < 16; ++k) {
+      const bool flag = (k == 11 || k == 12);
+      o[5 + k] = flag ? (int64_t)a[k] : (a[k] >= a[0] ? (int64_t)(a[k] - a[0]) : -1);
+    }
+    o[21] = o[22] = o[23] = 0;
     ++rows;
   }
   *n_rows = rows;

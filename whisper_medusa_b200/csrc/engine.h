@@ -13,13 +13,14 @@ struct DecModel;
 struct DecHostInfo {
   int n_sm;
   int H, K, n_layers, has_block;
+  int d;
   size_t smem;
   size_t smem_ring;
 };
 
 // ---- decode.cu ----
 size_t dec_smem_bytes(int d, int ffn);
-cudaError_t dec_configure(size_t smem, size_t smem_ring);
+cudaError_t dec_configure(int d, size_t smem, size_t smem_ring);
 size_t dec_ring_smem_bytes(int d);
 void dec_build_program(int n_layers, int has_block, std::vector<int>& flat, int off[4]);
 struct ChunkDesc;
