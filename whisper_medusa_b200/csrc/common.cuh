@@ -9,16 +9,20 @@
 #define WM_MAX_DEC_LAYERS 40
 #define WM_MAX_POS 512       // self-KV rows allocated per layer (448 + tree slack)
 #define WM_CROSS_CHUNKS 8    // cross-attention key chunks per head (flash-decoding split)
-#define WM_DEC_THREADS 480   // compute threads per decode CTA (15 warps; the ring kernel adds a producer warp -> 512)
+#define WM_DEC_THREADS 352   // compute threads per decode CTA (11 warps; the ring kernel adds a producer warp -> 384 => 168 registers)
 
 namespace wm {
 
 struct StageInstr;
-// one ring chunk: `nrows` (<= 16) weight rows of d fp16 columns, row r at src + r * row_bytes
+// one ring chunk: `nrows` (<= 16) rows of `copy_bytes` each, row r read at src + r * row_bytes and written at
+// slot + r * (slot row stride).  Weight chunks: rows of W (copy_bytes = d fp16); cross-attention chunks:
+// nrows = 1, one contiguous block of K or V rows.
 struct ChunkDesc {
   const void* src;
   uint32_t row_bytes;
   uint32_t nrows;
+  uint32_t copy_bytes;
+  uint32_t pad_;
 };
 
 // One stage of the persistent ring kernel, fully resolved for one CTA by the host (built once per
@@ -158,7 +162,8 @@ struct DecLayer {
   const float* fc2_b;
   __half* self_k;        // [WM_MAX_POS, d]
   __half* self_v;        // [WM_MAX_POS, d]
-  const __half* cross_kv;  // [S_pad, 2d]  (k | v), written by the encoder-side GEMM
+  const __half* cross_k;   // [H][S_pad][72]: 64 dims + 8 halfs of padding (the shared-memory row of the attention kernels)
+  const __half* cross_v;   // [H][S_pad][72]
 };
 
 // Loop state of one stream (device memory; the host only reads it back at sync points).

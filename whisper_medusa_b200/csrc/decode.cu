@@ -331,7 +331,7 @@ __device__ __noinline__ void stage_gemm(const GemmDesc& g, int cta, int ncta, un
 // -----------------------------------------------------------------------------------------
 #define WM_SA_MAXR 4
 __host__ __device__ constexpr size_t self_attn_smem_bytes() {
-  return (size_t)(WM_SA_MAXR * 64 + WM_SA_MAXR * WM_MAX_POS + 2 * WM_SA_MAXR + 60 * 64) * sizeof(float);
+  return (size_t)(WM_SA_MAXR * 64 + WM_SA_MAXR * WM_MAX_POS + 2 * WM_SA_MAXR + (WM_DEC_THREADS / 8) * 64) * sizeof(float);
 }
 __device__ __forceinline__ float dot64_h(const float* q, const uint4* kp) {
   float s = 0.f;
@@ -355,7 +355,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
   float* s_q = reinterpret_cast<float*>(smem_raw);                 // [R][64]
   float* s_p = s_q + WM_SA_MAXR * 64;                              // [R][WM_MAX_POS]
   float* s_st = s_p + WM_SA_MAXR * WM_MAX_POS;                     // [R] sum
-  float* s_acc = s_st + 2 * WM_SA_MAXR;                            // [60 groups][64]
+  float* s_acc = s_st + 2 * WM_SA_MAXR;                            // [WM_DEC_THREADS / 8 groups][64]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int R = (H * T + ncta - 1) / ncta;
   if (R > WM_SA_MAXR) R = WM_SA_MAXR;
@@ -396,8 +396,8 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
     cta_sync();
     // P * V : thread = (row r, key group kg, dim group dg of 8 dims)
     {
-      const int KG = 60 / rg;
-      const int dg = tid & 7, gI = tid >> 3;       // 60 groups of 8 threads
+      const int KG = (WM_DEC_THREADS / 8) / rg;
+      const int dg = tid & 7, gI = tid >> 3;       // groups of 8 threads
       const int r = gI / KG, kg = gI - r * KG;
       float a[8];
 #pragma unroll
@@ -440,7 +440,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
 #define WM_CH_PAD 224   // rounded up to the MMA k-step (16 keys)
 __host__ __device__ constexpr size_t cross_attn_smem_bytes() {
   return (size_t)2 * WM_CH_PAD * 72 * sizeof(__half) + (size_t)WM_MAX_T * WM_CH_PAD * sizeof(float) +
-         (size_t)2 * 16 * 72 * sizeof(__half) + (size_t)2 * WM_MAX_T * sizeof(float);
+         (size_t)2 * 16 * 72 * sizeof(__half) + (size_t)2 * WM_MAX_T * sizeof(float);   // K, V chunk + cross_scratch_bytes()
 }
 __device__ __forceinline__ void split_hilo(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
@@ -451,164 +451,225 @@ __device__ __forceinline__ void split_hilo(float a, float b, uint32_t& hi, uint3
 }
 // Both products run on the tensor cores (mma.sync m16n8k16, fp32 accumulate): S = Q K^T with the
 // fp32 query split into fp16 hi + lo, O = P V with the fp32 probabilities split the same way.
+//
+// cross_attn_core: one (head, key chunk) item once its K / V rows [nk_pad][72] (fp16, rows nk..nk_pad
+// zero) sit in shared memory -- in the scratch area (stage kernels) or in two ring slots (ring kernel).
+// `after_qk` / `after_pv` run once the last read of sK / sV is over (the ring hands the slots back there).
+struct CrossScratch {
+  float* sS;      // [16][CH_PAD] scores, then probabilities
+  __half* sQh;    // [16][72]
+  __half* sQl;
+  float* sM;      // [16] max, [16] sum
+};
+__host__ __device__ constexpr size_t cross_scratch_bytes() {
+  return (size_t)WM_MAX_T * WM_CH_PAD * sizeof(float) + (size_t)2 * 16 * 72 * sizeof(__half) + (size_t)2 * WM_MAX_T * sizeof(float);
+}
+__device__ __forceinline__ CrossScratch cross_scratch(unsigned char* p) {
+  CrossScratch cs;
+  cs.sS = reinterpret_cast<float*>(p);
+  cs.sQh = reinterpret_cast<__half*>(cs.sS + WM_MAX_T * WM_CH_PAD);
+  cs.sQl = cs.sQh + 16 * 72;
+  cs.sM = reinterpret_cast<float*>(cs.sQl + 16 * 72);
+  return cs;
+}
+template <class AfterQK, class AfterPV>
+__device__ __forceinline__ void cross_attn_core(const DecModel* m, int T, int h, int c, int nch, int nk, int nk_pad,
+                                                const __half* sK, const __half* sV, const CrossScratch& cs,
+                                                AfterQK&& after_qk, AfterPV&& after_pv) {
+  __shared__ int s_last;
+  float* sS = cs.sS; __half* sQh = cs.sQh; __half* sQl = cs.sQl; float* sM = cs.sM;
+  const int d = m->d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (WM_DEC_THREADS >> 5);
+  const int gq = lane >> 2, tq = lane & 3;
+  // queries (fp32) -> fp16 hi / lo, rows >= T are zero
+  for (int idx = tid; idx < 16 * 32; idx += WM_DEC_THREADS) {
+    const int r = idx >> 5, c2 = (idx & 31) * 2;
+    float a = 0.f, b = 0.f;
+    if (r < T) { const float2 v = ldcg_f2(m->q + (size_t)r * d + h * 64 + c2); a = v.x; b = v.y; }
+    uint32_t hi, lo;
+    split_hilo(a, b, hi, lo);
+    *reinterpret_cast<uint32_t*>(sQh + r * 72 + c2) = hi;
+    *reinterpret_cast<uint32_t*>(sQl + r * 72 + c2) = lo;
+  }
+  cta_sync();
+  // ---- S = Q K^T * head_dim^-0.5 : warp w takes key tiles (8 keys) w, w + nwarps, ... ----
+  {
+    uint32_t qh[4][4], ql[4][4];
+    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int ch = kk * 2 + (lane >> 4);
+      ldmatrix_x4(qh[kk][0], qh[kk][1], qh[kk][2], qh[kk][3], sQh + arow * 72 + ch * 8);
+      ldmatrix_x4(ql[kk][0], ql[kk][1], ql[kk][2], ql[kk][3], sQl + arow * 72 + ch * 8);
+    }
+    for (int nt = warp; nt < nk_pad / 8; nt += nwarps) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        uint32_t b0, b1, b2, b3;   // (keys nt*8.., k-steps 2*k2 and 2*k2+1)
+        ldmatrix_x4(b0, b1, b2, b3, sK + (nt * 8 + (lane & 7)) * 72 + (k2 * 4 + (lane >> 3)) * 8);
+        mma_16816(acc, qh[2 * k2][0], qh[2 * k2][1], qh[2 * k2][2], qh[2 * k2][3], b0, b1);
+        mma_16816(acc, ql[2 * k2][0], ql[2 * k2][1], ql[2 * k2][2], ql[2 * k2][3], b0, b1);
+        mma_16816(acc, qh[2 * k2 + 1][0], qh[2 * k2 + 1][1], qh[2 * k2 + 1][2], qh[2 * k2 + 1][3], b2, b3);
+        mma_16816(acc, ql[2 * k2 + 1][0], ql[2 * k2 + 1][1], ql[2 * k2 + 1][2], ql[2 * k2 + 1][3], b2, b3);
+      }
+      float* s0 = sS + gq * WM_CH_PAD + nt * 8 + 2 * tq;
+      s0[0] = acc[0] * 0.125f; s0[1] = acc[1] * 0.125f;
+      s0[8 * WM_CH_PAD] = acc[2] * 0.125f; s0[8 * WM_CH_PAD + 1] = acc[3] * 0.125f;
+    }
+  }
+  cta_sync();
+  after_qk();
+  // ---- per-row max / exp / sum : warp per row; rows >= T and keys >= nk become zero probability ----
+  for (int r = warp; r < 16; r += nwarps) {
+    float* p = sS + r * WM_CH_PAD;
+    if (r < T) {
+      float mx = -INFINITY;
+      for (int jj = lane; jj < nk; jj += 32) mx = fmaxf(mx, p[jj]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int jj = lane; jj < nk_pad; jj += 32) {
+        const float e = (jj < nk) ? expf(p[jj] - mx) : 0.f;
+        p[jj] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) { sM[r] = mx; sM[WM_MAX_T + r] = sum; }
+    } else {
+      for (int jj = lane; jj < nk_pad; jj += 32) p[jj] = 0.f;
+    }
+  }
+  cta_sync();
+  // ---- O = P V : warp w < 8 owns output dims w*8 .. w*8+7, all key steps ----
+  if (warp < 8) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ks = 0; ks < nk_pad / 16; ++ks) {
+      const float* p0 = sS + gq * WM_CH_PAD + ks * 16 + 2 * tq;
+      const float2 a00 = *reinterpret_cast<const float2*>(p0);
+      const float2 a10 = *reinterpret_cast<const float2*>(p0 + 8 * WM_CH_PAD);
+      const float2 a01 = *reinterpret_cast<const float2*>(p0 + 8);
+      const float2 a11 = *reinterpret_cast<const float2*>(p0 + 8 * WM_CH_PAD + 8);
+      uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+      split_hilo(a00.x, a00.y, h0, l0);   // row g,   keys 2t..2t+1
+      split_hilo(a10.x, a10.y, h1, l1);   // row g+8
+      split_hilo(a01.x, a01.y, h2, l2);   // row g,   keys 2t+8..
+      split_hilo(a11.x, a11.y, h3, l3);   // row g+8
+      uint32_t b0, b1;
+      ldmatrix_x2_trans(b0, b1, sV + (ks * 16 + (lane & 15)) * 72 + warp * 8);
+      mma_16816(acc, h0, h1, h2, h3, b0, b1);
+      mma_16816(acc, l0, l1, l2, l3, b0, b1);
+    }
+    float* out0 = m->cross_part + ((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + gq) * (WM_HEAD_DIM + 2) + warp * 8 + 2 * tq;
+    if (gq < T) { out0[0] = acc[0]; out0[1] = acc[1]; }
+    if (gq + 8 < T) { out0[8 * (WM_HEAD_DIM + 2)] = acc[2]; out0[8 * (WM_HEAD_DIM + 2) + 1] = acc[3]; }
+  }
+  if (tid < T) {
+    float* out = m->cross_part + ((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + tid) * (WM_HEAD_DIM + 2);
+    out[64] = sM[tid];
+    out[65] = sM[WM_MAX_T + tid];
+  }
+  // fold: the chunk that arrives last for this head (always in chunk order => deterministic)
+  // (release-only arrival; the partials are read back with L2-coherent loads, see common.cuh)
+  cta_sync();
+  after_pv();
+  if (tid == 0) {
+    const unsigned int prev = atom_add_release(&m->cross_cnt[h], 1u);
+    s_last = (prev == (unsigned int)(nch - 1)) ? 1 : 0;
+    if (s_last) m->cross_cnt[h] = 0u;   // everybody has arrived: re-arm for the next layer
+  }
+  cta_sync();
+  if (s_last) {
+    const size_t cstride = (size_t)WM_MAX_T * (WM_HEAD_DIM + 2);
+    for (int idx = tid; idx < T * 64; idx += WM_DEC_THREADS) {
+      const int rr = idx >> 6, e = idx & 63;
+      const float* base = m->cross_part + ((size_t)h * WM_CROSS_CHUNKS * WM_MAX_T + rr) * (WM_HEAD_DIM + 2);
+      // every load of the element in flight at once (a loop with a run-time bound would pay one L2 round trip per chunk)
+      float mv[WM_CROSS_CHUNKS], lv[WM_CROSS_CHUNKS], vv[WM_CROSS_CHUNKS];
+#pragma unroll
+      for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc)
+        if (cc < nch) {
+          mv[cc] = __ldcg(base + cc * cstride + 64);
+          lv[cc] = __ldcg(base + cc * cstride + 65);
+          vv[cc] = __ldcg(base + cc * cstride + e);
+        }
+      float M = -INFINITY;
+#pragma unroll
+      for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc)
+        if (cc < nch) M = fmaxf(M, mv[cc]);
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc)
+        if (cc < nch) {
+          const float w = expf(mv[cc] - M);
+          num = fmaf(w, vv[cc], num);
+          den = fmaf(w, lv[cc], den);
+        }
+      m->attn[(size_t)rr * d + h * 64 + e] = num / den;
+    }
+  }
+}
+
 __device__ __forceinline__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
   const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
-  const int d = m->d, H = m->H, S = m->S;
+  const int H = m->H, S = m->S;
   const DecLayer& L = m->layers[layer];
   const int nch = m->cross_chunks;
   const int CH = (S + nch - 1) / nch;
   __half* sK = reinterpret_cast<__half*>(smem_raw);                 // [CH_PAD][72]
   __half* sV = sK + WM_CH_PAD * 72;                                 // [CH_PAD][72]
-  float* sS = reinterpret_cast<float*>(sV + WM_CH_PAD * 72);        // [16][CH_PAD]  scores, then probabilities
-  __half* sQh = reinterpret_cast<__half*>(sS + WM_MAX_T * WM_CH_PAD);   // [16][72]
-  __half* sQl = sQh + 16 * 72;
-  float* sM = reinterpret_cast<float*>(sQl + 16 * 72);              // [16] max, [16] sum
-  __shared__ int s_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (WM_DEC_THREADS >> 5);
-  const int gq = lane >> 2, tq = lane & 3;
-  const int T = g.T;
+  const CrossScratch cs = cross_scratch(reinterpret_cast<unsigned char*>(sV + WM_CH_PAD * 72));
+  const int tid = threadIdx.x;
   for (int item = cta; item < H * nch; item += ncta) {
     const int h = item / nch, c = item - h * nch;
     const int j0 = c * CH, nk = max(0, min(S, j0 + CH) - j0);
     const int nk_pad = (nk + 15) & ~15;
     cta_sync();
-    // K / V chunk -> shared memory (all loads of a batch in flight before the first store)
-    for (int base = 0; base < nk * 8; base += 4 * WM_DEC_THREADS) {
+    // K / V chunk -> shared memory (all loads of a batch in flight before the first store); the cache rows are
+    // already in the shared-memory layout: cross_k[h][pos][72]
+    const uint4* gk = reinterpret_cast<const uint4*>(L.cross_k + ((size_t)h * m->S_pad + j0) * 72);
+    const uint4* gv = reinterpret_cast<const uint4*>(L.cross_v + ((size_t)h * m->S_pad + j0) * 72);
+    for (int base = 0; base < nk * 9; base += 4 * WM_DEC_THREADS) {
       uint4 kk[4], vv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int idx = base + i * WM_DEC_THREADS + tid;
-        if (idx < nk * 8) {
-          const __half* src = L.cross_kv + (size_t)(j0 + (idx >> 3)) * 2 * d + h * 64 + (idx & 7) * 8;
-          kk[i] = ldg_nc_v4(src);
-          vv[i] = ldg_nc_v4(src + d);
-        }
+        if (idx < nk * 9) { kk[i] = ldg_nc_v4(gk + idx); vv[i] = ldg_nc_v4(gv + idx); }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int idx = base + i * WM_DEC_THREADS + tid;
-        if (idx < nk * 8) {
-          *reinterpret_cast<uint4*>(sK + (idx >> 3) * 72 + (idx & 7) * 8) = kk[i];
-          *reinterpret_cast<uint4*>(sV + (idx >> 3) * 72 + (idx & 7) * 8) = vv[i];
+        if (idx < nk * 9) {
+          reinterpret_cast<uint4*>(sK)[idx] = kk[i];
+          reinterpret_cast<uint4*>(sV)[idx] = vv[i];
         }
       }
     }
     // rows nk .. nk_pad of K and V read as zero (their probabilities are zero, but 0 * garbage could be NaN)
-    for (int idx = tid; idx < (nk_pad - nk) * 8; idx += WM_DEC_THREADS) {
-      *reinterpret_cast<uint4*>(sK + (nk + (idx >> 3)) * 72 + (idx & 7) * 8) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sV + (nk + (idx >> 3)) * 72 + (idx & 7) * 8) = make_uint4(0, 0, 0, 0);
+    for (int idx = tid; idx < (nk_pad - nk) * 9; idx += WM_DEC_THREADS) {
+      reinterpret_cast<uint4*>(sK)[nk * 9 + idx] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(sV)[nk * 9 + idx] = make_uint4(0, 0, 0, 0);
     }
-    // queries (fp32) -> fp16 hi / lo, rows >= T are zero
-    for (int idx = tid; idx < 16 * 32; idx += WM_DEC_THREADS) {
-      const int r = idx >> 5, c2 = (idx & 31) * 2;
-      float a = 0.f, b = 0.f;
-      if (r < T) { const float2 v = ldcg_f2(m->q + (size_t)r * d + h * 64 + c2); a = v.x; b = v.y; }
-      uint32_t hi, lo;
-      split_hilo(a, b, hi, lo);
-      *reinterpret_cast<uint32_t*>(sQh + r * 72 + c2) = hi;
-      *reinterpret_cast<uint32_t*>(sQl + r * 72 + c2) = lo;
+    cross_attn_core(m, g.T, h, c, nch, nk, nk_pad, sK, sV, cs, [] {}, [] {});
+  }
+}
+
+// Encoder side: cross K/V of one decoder layer from the GEMM layout [pos][k | v] into the decode layout
+// cross_k / cross_v [H][S_pad][72] (64 dims + 8 halfs of padding = the bank-conflict-free shared-memory row).
+__global__ void __launch_bounds__(256) relayout_cross_kv_kernel(const __half* __restrict__ kv, __half* __restrict__ ck,
+                                                                __half* __restrict__ cv, int S, int S_pad, int d, int H) {
+  const size_t total = (size_t)H * S_pad * 9;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % 9);
+    const size_t row = i / 9;
+    const int pos = (int)(row % S_pad), h = (int)(row / S_pad);
+    uint4 k = make_uint4(0, 0, 0, 0), v = k;
+    if (q < 8 && pos < S) {
+      const __half* src = kv + (size_t)pos * 2 * d + h * 64 + q * 8;
+      k = *reinterpret_cast<const uint4*>(src);
+      v = *reinterpret_cast<const uint4*>(src + d);
     }
-    cta_sync();
-    // ---- S = Q K^T * head_dim^-0.5 : warp w takes key tiles (8 keys) w, w + nwarps, ... ----
-    {
-      uint32_t qh[4][4], ql[4][4];
-      const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int ch = kk * 2 + (lane >> 4);
-        ldmatrix_x4(qh[kk][0], qh[kk][1], qh[kk][2], qh[kk][3], sQh + arow * 72 + ch * 8);
-        ldmatrix_x4(ql[kk][0], ql[kk][1], ql[kk][2], ql[kk][3], sQl + arow * 72 + ch * 8);
-      }
-      for (int nt = warp; nt < nk_pad / 8; nt += nwarps) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int k2 = 0; k2 < 2; ++k2) {
-          uint32_t b0, b1, b2, b3;   // (keys nt*8.., k-steps 2*k2 and 2*k2+1)
-          ldmatrix_x4(b0, b1, b2, b3, sK + (nt * 8 + (lane & 7)) * 72 + (k2 * 4 + (lane >> 3)) * 8);
-          mma_16816(acc, qh[2 * k2][0], qh[2 * k2][1], qh[2 * k2][2], qh[2 * k2][3], b0, b1);
-          mma_16816(acc, ql[2 * k2][0], ql[2 * k2][1], ql[2 * k2][2], ql[2 * k2][3], b0, b1);
-          mma_16816(acc, qh[2 * k2 + 1][0], qh[2 * k2 + 1][1], qh[2 * k2 + 1][2], qh[2 * k2 + 1][3], b2, b3);
-          mma_16816(acc, ql[2 * k2 + 1][0], ql[2 * k2 + 1][1], ql[2 * k2 + 1][2], ql[2 * k2 + 1][3], b2, b3);
-        }
-        float* s0 = sS + gq * WM_CH_PAD + nt * 8 + 2 * tq;
-        s0[0] = acc[0] * 0.125f; s0[1] = acc[1] * 0.125f;
-        s0[8 * WM_CH_PAD] = acc[2] * 0.125f; s0[8 * WM_CH_PAD + 1] = acc[3] * 0.125f;
-      }
-    }
-    cta_sync();
-    // ---- per-row max / exp / sum : warp per row; rows >= T and keys >= nk become zero probability ----
-    for (int r = warp; r < 16; r += nwarps) {
-      float* p = sS + r * WM_CH_PAD;
-      if (r < T) {
-        float mx = -INFINITY;
-        for (int jj = lane; jj < nk; jj += 32) mx = fmaxf(mx, p[jj]);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int jj = lane; jj < nk_pad; jj += 32) {
-          const float e = (jj < nk) ? expf(p[jj] - mx) : 0.f;
-          p[jj] = e;
-          sum += e;
-        }
-        sum = warp_sum(sum);
-        if (lane == 0) { sM[r] = mx; sM[WM_MAX_T + r] = sum; }
-      } else {
-        for (int jj = lane; jj < nk_pad; jj += 32) p[jj] = 0.f;
-      }
-    }
-    cta_sync();
-    // ---- O = P V : warp w < 8 owns output dims w*8 .. w*8+7, all key steps ----
-    if (warp < 8) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int ks = 0; ks < nk_pad / 16; ++ks) {
-        const float* p0 = sS + gq * WM_CH_PAD + ks * 16 + 2 * tq;
-        const float2 a00 = *reinterpret_cast<const float2*>(p0);
-        const float2 a10 = *reinterpret_cast<const float2*>(p0 + 8 * WM_CH_PAD);
-        const float2 a01 = *reinterpret_cast<const float2*>(p0 + 8);
-        const float2 a11 = *reinterpret_cast<const float2*>(p0 + 8 * WM_CH_PAD + 8);
-        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-        split_hilo(a00.x, a00.y, h0, l0);   // row g,   keys 2t..2t+1
-        split_hilo(a10.x, a10.y, h1, l1);   // row g+8
-        split_hilo(a01.x, a01.y, h2, l2);   // row g,   keys 2t+8..
-        split_hilo(a11.x, a11.y, h3, l3);   // row g+8
-        uint32_t b0, b1;
-        ldmatrix_x2_trans(b0, b1, sV + (ks * 16 + (lane & 15)) * 72 + warp * 8);
-        mma_16816(acc, h0, h1, h2, h3, b0, b1);
-        mma_16816(acc, l0, l1, l2, l3, b0, b1);
-      }
-      float* out0 = m->cross_part + ((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + gq) * (WM_HEAD_DIM + 2) + warp * 8 + 2 * tq;
-      if (gq < T) { out0[0] = acc[0]; out0[1] = acc[1]; }
-      if (gq + 8 < T) { out0[8 * (WM_HEAD_DIM + 2)] = acc[2]; out0[8 * (WM_HEAD_DIM + 2) + 1] = acc[3]; }
-    }
-    if (tid < T) {
-      float* out = m->cross_part + ((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + tid) * (WM_HEAD_DIM + 2);
-      out[64] = sM[tid];
-      out[65] = sM[WM_MAX_T + tid];
-    }
-    // fold: the chunk that arrives last for this head (always in chunk order => deterministic)
-    // (release-only arrival; the partials are read back with L2-coherent loads, see common.cuh)
-    cta_sync();
-    if (tid == 0) {
-      const unsigned int prev = atom_add_release(&m->cross_cnt[h], 1u);
-      s_last = (prev == (unsigned int)(nch - 1)) ? 1 : 0;
-      if (s_last) m->cross_cnt[h] = 0u;   // everybody has arrived: re-arm for the next layer
-    }
-    cta_sync();
-    if (s_last) {
-      const size_t cstride = (size_t)WM_MAX_T * (WM_HEAD_DIM + 2);
-      for (int idx = tid; idx < T * 64; idx += WM_DEC_THREADS) {
-        const int rr = idx >> 6, e = idx & 63;
-        const float* base = m->cross_part + ((size_t)h * WM_CROSS_CHUNKS * WM_MAX_T + rr) * (WM_HEAD_DIM + 2);
-        float M = -INFINITY;
-        for (int cc = 0; cc < nch; ++cc) M = fmaxf(M, __ldcg(base + cc * cstride + 64));
-        float num = 0.f, den = 0.f;
-        for (int cc = 0; cc < nch; ++cc) {
-          const float w = expf(__ldcg(base + cc * cstride + 64) - M);
-          num = fmaf(w, __ldcg(base + cc * cstride + e), num);
-          den = fmaf(w, __ldcg(base + cc * cstride + 65), den);
-        }
-        m->attn[(size_t)rr * d + h * 64 + e] = num / den;
-      }
-    }
+    reinterpret_cast<uint4*>(ck)[i] = k;
+    reinterpret_cast<uint4*>(cv)[i] = v;
   }
 }
 
@@ -769,19 +830,28 @@ __device__ __noinline__ void stage_select1(const DecModel* m, int mode, int cta,
   }
 }
 
-// fold the segment partials of row r: global max (first index on ties) and normaliser
-__device__ __forceinline__ void select_fold(const DecModel* m, int r, int nseg, float inv_t, float& M, int& idx, float& Z) {
-  const float* p = m->sel_part + (size_t)r * WM_SEL_MAXSEG * 4;
+// fold the segment partials of row r: global max (first index on ties), normaliser and the sum of the entropy
+// partials.  Warp-cooperative (call with all 32 lanes): lane sg fetches segment sg with one 16-byte L2 load --
+// one round trip instead of one per segment -- and the fold walks the lanes in segment order (shuffles), so the
+// summation order is that of a sequential loop.  Results are uniform across the warp.
+__device__ __forceinline__ void select_fold(const DecModel* m, int r, int nseg, float inv_t, float& M, int& idx, float& Z,
+                                            float& ent) {
+  const int lane = threadIdx.x & 31;
+  float4 q = make_float4(-INFINITY, 0.f, 0.f, 0.f);
+  if (lane < nseg) q = __ldcg(reinterpret_cast<const float4*>(m->sel_part + (size_t)r * WM_SEL_MAXSEG * 4) + lane);
   M = -INFINITY; idx = 0x7fffffff;
   for (int sg = 0; sg < nseg; ++sg) {
-    const float v = __ldcg(p + sg * 4);
-    const int i = __float_as_int(__ldcg(p + sg * 4 + 1));
+    const float v = __shfl_sync(0xffffffffu, q.x, sg);
+    const int i = __float_as_int(__shfl_sync(0xffffffffu, q.y, sg));
     if (v > M || (v == M && i < idx)) { M = v; idx = i; }
   }
-  Z = 0.f;
+  Z = 0.f; ent = 0.f;
+  const float w = (q.x > -INFINITY) ? q.z * expf((q.x - M) * inv_t) : 0.f;   // this lane's term (uniform M)
   for (int sg = 0; sg < nseg; ++sg) {
-    const float v = __ldcg(p + sg * 4);
-    if (v > -INFINITY) Z += __ldcg(p + sg * 4 + 2) * expf((v - M) * inv_t);
+    const float v = __shfl_sync(0xffffffffu, q.x, sg);
+    const float t = __shfl_sync(0xffffffffu, w, sg);
+    if (v > -INFINITY) Z += t;
+    ent += __shfl_sync(0xffffffffu, q.w, sg);
   }
 }
 
@@ -802,8 +872,8 @@ __device__ __noinline__ void stage_select2(const DecModel* m, int cta, int ncta,
     const int r = item / nseg, sg = item - r * nseg;
     const int j0 = sg * seglen, j1 = min(V, j0 + seglen);
     const float* row = m->logits_b + (size_t)r * V;
-    float M, Z; int idx;
-    select_fold(m, r, nseg, inv_t, M, idx, Z);
+    float M, Z, ent_unused; int idx;
+    select_fold(m, r, nseg, inv_t, M, idx, Z, ent_unused);   // (every warp folds the same row: uniform)
     float ent = 0.f;
     for (int j = j0 + threadIdx.x; j < j1; j += WM_DEC_THREADS) {
       const float p = expf((processed_logit(row, j, m->tok_mask, begin_on, eos, pen) - M) * inv_t) / Z;
@@ -820,13 +890,13 @@ __device__ __noinline__ void stage_select2(const DecModel* m, int cta, int ncta,
 }
 
 // tail: candidates = top-1 of every head row (generate_candidates, medusa_utils.py:446-457)
-__device__ void stage_select_fin(const DecModel* m, int ncta) {
+__device__ __noinline__ void stage_select_fin(const DecModel* m, int ncta) {
   DecState* st = m->st;
   const int nseg = select_nseg(m, ncta);
-  if (threadIdx.x <= m->K) {
-    float M, Z; int idx;
-    select_fold(m, threadIdx.x, nseg, 1.0f, M, idx, Z);
-    st->cand[threadIdx.x] = idx;
+  for (int r = threadIdx.x >> 5; r <= m->K; r += (WM_DEC_THREADS >> 5)) {   // warp per row
+    float M, Z, ent; int idx;
+    select_fold(m, r, nseg, 1.0f, M, idx, Z, ent);
+    if ((threadIdx.x & 31) == 0) st->cand[r] = idx;
   }
 }
 
@@ -850,16 +920,14 @@ __device__ __noinline__ void stage_accept(const DecModel* m, int ncta) {
   const int K = m->K;
   const int nseg = select_nseg(m, ncta);
   // fold the scan partials: argmax of every row, acceptance threshold of rows < K
-  if (threadIdx.x <= K) {
-    const int r = threadIdx.x;
+  for (int r = threadIdx.x >> 5; r <= K; r += (WM_DEC_THREADS >> 5)) {   // warp per row
     const float temp = st->temperature;
-    float M, Z; int idx;
-    select_fold(m, r, nseg, temp > 0.f ? 1.0f / temp : 1.0f, M, idx, Z);
-    st->row_argmax[r] = idx;
-    if (r < K && temp > 0.f) {
-      float ent = 0.f;
-      for (int sg = 0; sg < nseg; ++sg) ent += __ldcg(m->sel_part + ((size_t)r * WM_SEL_MAXSEG + sg) * 4 + 3);
-      st->row_thr[r] = fminf(st->post_thr, expf(ent) * st->post_alpha);   // ent = sum p log(p+1e-5) = -entropy
+    float M, Z, ent; int idx;
+    select_fold(m, r, nseg, temp > 0.f ? 1.0f / temp : 1.0f, M, idx, Z, ent);
+    if ((threadIdx.x & 31) == 0) {
+      st->row_argmax[r] = idx;
+      if (r < K && temp > 0.f)
+        st->row_thr[r] = fminf(st->post_thr, expf(ent) * st->post_alpha);   // ent = sum p log(p+1e-5) = -entropy
     }
   }
   cta_sync();
@@ -1143,6 +1211,22 @@ void dec_build_chunk_table(const DecModel& hm, int ncta, std::vector<ChunkDesc>&
       off[(size_t)cta * 4 + list] = (int)tab.size();
       for (int ip = poff[list]; ip < poff[list + 1]; ++ip) {
         const int stage = flat[ip * 3], mode = flat[ip * 3 + 1], layer = flat[ip * 3 + 2];
+        if (stage == ST_CROSS_ATTN) {
+          // the K and the V rows of every (head, key chunk) item of this CTA: one contiguous copy each
+          const int nch = hm.cross_chunks, CH = (hm.S + nch - 1) / nch;
+          for (int item = cta; item < hm.H * nch; item += ncta) {
+            const int hh = item / nch, cc = item - hh * nch;
+            const int j0 = cc * CH, nk = std::max(0, std::min(hm.S, j0 + CH) - j0);
+            if (nk == 0) continue;
+            ChunkDesc c;
+            c.row_bytes = 0; c.nrows = 1; c.copy_bytes = (uint32_t)(nk * 72 * sizeof(__half));
+            c.src = hm.layers[layer].cross_k + ((size_t)hh * hm.S_pad + j0) * 72;
+            tab.push_back(c);
+            c.src = hm.layers[layer].cross_v + ((size_t)hh * hm.S_pad + j0) * 72;
+            tab.push_back(c);
+          }
+          continue;
+        }
         if (!is_gemm_stage(stage)) continue;
         const WDesc w = stage_weights(&hm, stage, mode, layer);
         const GemmWork wk = gemm_work(w.N, w.K, hm.d, cta, ncta);
@@ -1153,6 +1237,7 @@ void dec_build_chunk_table(const DecModel& hm, int ncta, std::vector<ChunkDesc>&
           c.src = w.W + (size_t)(wk.n_begin + u * 16) * w.K + (size_t)wk.seg * hm.d;
           c.row_bytes = (uint32_t)(w.K * sizeof(__half));
           c.nrows = (uint32_t)std::min(16, wk.n_rows - u * 16);
+          c.copy_bytes = (uint32_t)(hm.d * sizeof(__half));
           tab.push_back(c);
         }
       }
@@ -1212,6 +1297,13 @@ void dec_build_stage_table(const DecModel& hm, int ncta, std::vector<CtaStage>& 
       c.segs = wk.segs; c.seg = wk.seg; c.block = wk.block;
     }
   }
+}
+
+cudaError_t dec_relayout_cross_kv(const __half* kv, __half* ck, __half* cv, int S, int S_pad, int d, int H, cudaStream_t s,
+                                  int64_t* n_launch) {
+  relayout_cross_kv_kernel<<<296, 256, 0, s>>>(kv, ck, cv, S, S_pad, d, H);
+  if (n_launch) ++*n_launch;
+  return cudaGetLastError();
 }
 
 cudaError_t dec_launch_iteration_ring(const DecModel* dm, const DecHostInfo& hi, bool profile, cudaStream_t s) {

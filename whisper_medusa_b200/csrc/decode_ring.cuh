@@ -140,7 +140,8 @@ template <int D>
 struct RingGeom {
   static_assert(D % 32 == 0 && D <= 1280, "decoder width must be a multiple of 32, at most 1280");
   static constexpr int ROW_STRIDE = D * 2 + 64;       // ring row stride, bytes
-  static constexpr int SLOT_BYTES = 16 * ROW_STRIDE;
+  // a slot holds 16 weight rows or the K (or V) rows of one cross-attention key chunk ([CH_PAD][72] fp16)
+  static constexpr int SLOT_BYTES = (int)round128(cmax((size_t)16 * ROW_STRIDE, (size_t)WM_CH_PAD * 72 * sizeof(__half)));
   static constexpr int XS = D * 4 + WM_XS_PADB;       // activation row stride, bytes
   static constexpr int NKS = ring_nks(D);             // k-slices per chunk (one MMA warp each)
   static constexpr int KS = D / NKS;
@@ -149,7 +150,7 @@ struct RingGeom {
   static constexpr int NV = (D + 127) / 128;          // float4 per lane of a row-per-warp pass
   // shared-memory map
   static constexpr size_t SCRATCH_OFF = (size_t)WM_RING_G * SLOT_BYTES;
-  static constexpr size_t SCRATCH = round128(cmax(cmax((size_t)16 * XS, cross_attn_smem_bytes()), self_attn_smem_bytes()));
+  static constexpr size_t SCRATCH = round128(cmax(cmax((size_t)16 * XS, cross_scratch_bytes()), self_attn_smem_bytes()));
   static constexpr size_t PARTIAL_OFF = SCRATCH_OFF + SCRATCH;
   static constexpr size_t PARTIAL = round128(cmax((size_t)8 * 256 * sizeof(float), (size_t)2 * D * sizeof(float)));
   static constexpr size_t MODEL_OFF = PARTIAL_OFF + PARTIAL;
@@ -176,12 +177,12 @@ __device__ __noinline__ void ring_producer(unsigned char* ring, uint64_t* full, 
     if (lane == 0) {
       while (!mbar_try_wait(empty + slot, par)) { }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the slot vs async writes
-      mbar_expect_tx(full + slot, (uint32_t)(dsc.nrows * D * 2));
+      mbar_expect_tx(full + slot, dsc.nrows * dsc.copy_bytes);
     }
     __syncwarp();
     if (lane < dsc.nrows) {
       bulk_g2s(ring + (size_t)slot * G::SLOT_BYTES + (size_t)lane * G::ROW_STRIDE,
-               reinterpret_cast<const unsigned char*>(dsc.src) + (size_t)lane * dsc.row_bytes, (uint32_t)(D * 2), full + slot);
+               reinterpret_cast<const unsigned char*>(dsc.src) + (size_t)lane * dsc.row_bytes, dsc.copy_bytes, full + slot);
     }
     __syncwarp();
     if (++slot == WM_RING_G) { slot = 0; par ^= 1u; }
@@ -436,13 +437,65 @@ __device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* sm
       for (int t = warp; t < T; t += nwarps) {
         for (int r = lane; r < n_rows; r += 32) {
           const int row = n_begin + r;
-          float s = 0.f;
-          for (int sg = 0; sg < segs; ++sg) s += __ldcg(m->gemm_part + ((size_t)sg * 16 + t) * N + row);
           float* o = out + (size_t)t * ldo + row;
-          *o = ldcg_f(o) + (s + (bias ? bias[row] : 0.f));
+          // all loads in flight together (batches of 4 segments), summed in segment order
+          const float xo = ldcg_f(o);
+          const float bv = bias ? bias[row] : 0.f;
+          float s = 0.f;
+          for (int s0 = 0; s0 < segs; s0 += 4) {
+            float pv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (s0 + i < segs) pv[i] = __ldcg(m->gemm_part + ((size_t)(s0 + i) * 16 + t) * N + row);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (s0 + i < segs) s += pv[i];
+          }
+          *o = xo + (s + bv);
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-attention fed from the ring: the K rows and the V rows of this CTA's (head, key chunk) item
+// arrive as two ring chunks, prefetched by the producer while the preceding stages run; the MMAs
+// read them in place (the cache rows already have the 72-half shared-memory stride).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void stage_cross_attn_ring(RingState& rs, unsigned char* smem, const DecModel* m, int T, int cta, int ncta) {
+  using G = RingGeom<D>;
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem + G::BAR_OFF);
+  uint64_t* const empty = full + WM_RING_G;
+  const CrossScratch cs = cross_scratch(smem + G::SCRATCH_OFF);
+  const int H = m->H, S = m->S, nch = m->cross_chunks;
+  const int CH = (S + nch - 1) / nch;
+  const int tid = threadIdx.x;
+  for (int item = cta; item < H * nch; item += ncta) {
+    const int h = item / nch, c = item - h * nch;
+    const int j0 = c * CH, nk = max(0, min(S, j0 + CH) - j0);
+    if (nk == 0) continue;   // (no chunks in the table either)
+    const int nk_pad = (nk + 15) & ~15;
+    const int slot_k = rs.slot;
+    const unsigned int par_k = rs.par;
+    if (++rs.slot == WM_RING_G) { rs.slot = 0; rs.par ^= 1u; }
+    const int slot_v = rs.slot;
+    const unsigned int par_v = rs.par;
+    if (++rs.slot == WM_RING_G) { rs.slot = 0; rs.par ^= 1u; }
+    __half* sK = reinterpret_cast<__half*>(smem + (size_t)slot_k * G::SLOT_BYTES);
+    __half* sV = reinterpret_cast<__half*>(smem + (size_t)slot_v * G::SLOT_BYTES);
+    while (!mbar_try_wait(full + slot_k, par_k)) { }
+    while (!mbar_try_wait(full + slot_v, par_v)) { }
+    // rows nk .. nk_pad read as zero (their probabilities are zero, but 0 * stale bits could be NaN)
+    for (int idx = tid; idx < (nk_pad - nk) * 9; idx += WM_DEC_THREADS) {
+      reinterpret_cast<uint4*>(sK)[nk * 9 + idx] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(sV)[nk * 9 + idx] = make_uint4(0, 0, 0, 0);
+    }
+    cross_attn_core(
+        m, T, h, c, nch, nk, nk_pad, sK, sV, cs,
+        [&] { if (tid == 0) mbar_arrive(empty + slot_k); },
+        [&] { if (tid == 0) mbar_arrive(empty + slot_v); });
   }
 }
 
@@ -517,6 +570,8 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
     else { pgv.T = 1; pgv.base = L0 - 1; }
     if (is_gemm_stage(stage)) {
       stage_gemm_ring<D>(rs, smem, m, sd, pgv.T, pgv.base, pr);
+    } else if (stage == ST_CROSS_ATTN) {
+      stage_cross_attn_ring<D>(rs, smem, m, pgv.T, cta, ncta);
     } else {
       run_stage<false>(m, stage, mode, sd->layer, cta, ncta, smem + G::SCRATCH_OFF, &pgv);
     }

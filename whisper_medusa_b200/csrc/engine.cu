@@ -52,7 +52,7 @@ struct wm_handle {
   __half *x_tm = nullptr, *h1 = nullptr, *ln16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *ffn16 = nullptr,
          *enc16 = nullptr;
   int* gmax = nullptr;
-  std::vector<__half*> cross_kv, self_k, self_v;
+  std::vector<__half*> cross_k, cross_v, self_k, self_v;
   // decode buffers
   DecModel hm;             // host copy
   DecModel* dm = nullptr;  // device copy
@@ -244,11 +244,13 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   CK(dalloc(&h->att16, SP * d));
   CK(dalloc(&h->ffn16, SP * f));
   CK(dalloc(&h->enc16, SP * d));
-  h->cross_kv.resize(h->n_dec);
+  h->cross_k.resize(h->n_dec);
+  h->cross_v.resize(h->n_dec);
   h->self_k.resize(h->n_dec);
   h->self_v.resize(h->n_dec);
   for (int i = 0; i < h->n_dec; ++i) {
-    CK(dalloc(&h->cross_kv[i], SP * 2 * d));
+    CK(dalloc(&h->cross_k[i], (size_t)c.n_heads * SP * 72));
+    CK(dalloc(&h->cross_v[i], (size_t)c.n_heads * SP * 72));
     CK(dalloc(&h->self_k[i], (size_t)WM_MAX_POS * d));
     CK(dalloc(&h->self_v[i], (size_t)WM_MAX_POS * d));
   }
@@ -326,7 +328,8 @@ extern "C" int wm_destroy(wm_handle* h) {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(h->pcm); F(h->mel32); F(h->melfb); F(h->gmax); F(h->x_tm); F(h->h1); F(h->x32); F(h->enc32); F(h->ln16);
   F(h->qkv16); F(h->att16); F(h->ffn16); F(h->enc16);
-  for (auto p : h->cross_kv) F(p);
+  for (auto p : h->cross_k) F(p);
+  for (auto p : h->cross_v) F(p);
   for (auto p : h->self_k) F(p);
   for (auto p : h->self_v) F(p);
   F(h->hm.x); F(h->hm.q); F(h->hm.attn); F(h->hm.ffn_h); F(h->hm.hidden); F(h->hm.head_h); F(h->hm.carry); F(h->hm.cross_part); F(h->hm.cross_cnt); F(h->hm.sel_part); F(h->hm.gemm_part); F(h->hm.gemm_cnt);
@@ -387,7 +390,7 @@ static int bind_weights(wm_handle* h) {
     L.ln3_g = wptr<float>(h, p + "ln3_g"); L.ln3_b = wptr<float>(h, p + "ln3_b");
     L.fc1_w = wptr<__half>(h, p + "fc1_w"); L.fc1_b = wptr<float>(h, p + "fc1_b");
     L.fc2_w = wptr<__half>(h, p + "fc2_w"); L.fc2_b = wptr<float>(h, p + "fc2_b");
-    L.self_k = h->self_k[i]; L.self_v = h->self_v[i]; L.cross_kv = h->cross_kv[i];
+    L.self_k = h->self_k[i]; L.self_v = h->self_v[i]; L.cross_k = h->cross_k[i]; L.cross_v = h->cross_v[i];
   }
   m.embed = wptr<__half>(h, "dec.embed");
   m.pos = wptr<float>(h, "dec.pos");
@@ -504,13 +507,14 @@ static int run_encoder(wm_handle* h) {
     CK(gemm_dispatch(h, a, s, nl));
   }
   CK(enc_layernorm(h->x32, wptr<float>(h, "enc.lnf_g"), wptr<float>(h, "enc.lnf_b"), h->enc16, h->enc32, S, d, s, nl));
-  // cross-attention K/V of every decoder layer, written in the decode layout [pos][k | v]
+  // cross-attention K/V of every decoder layer, re-laid out per head for the decode kernels (cross_k / cross_v)
   for (int i = 0; i < h->n_dec; ++i) {
     std::string p = "dec." + std::to_string(i) + ".";
     memset(&a, 0, sizeof a);
     a.A = h->enc16; a.lda = d; a.W = wptr<__half>(h, p + "ckv_w"); a.bias = wptr<float>(h, p + "ckv_b");
-    a.M = S; a.N = 2 * d; a.K = d; a.epi = ENC_EPI_BIAS_F16; a.out16 = h->cross_kv[i]; a.ldo16 = 2 * d;
+    a.M = S; a.N = 2 * d; a.K = d; a.epi = ENC_EPI_BIAS_F16; a.out16 = h->qkv16; a.ldo16 = 2 * d;   // (scratch: [pos][k | v])
     CK(gemm_dispatch(h, a, s, nl));
+    CK(dec_relayout_cross_kv(h->qkv16, h->cross_k[i], h->cross_v[i], S, h->S_pad, d, h->cfg.n_heads, s, nl));
   }
   return WM_OK;
 }

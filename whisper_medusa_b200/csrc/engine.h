@@ -25,6 +25,8 @@ size_t dec_ring_smem_bytes(int d);
 void dec_build_program(int n_layers, int has_block, std::vector<int>& flat, int off[4]);
 struct ChunkDesc;
 void dec_build_chunk_table(const DecModel& hm, int ncta, std::vector<ChunkDesc>& tab, std::vector<int>& off);
+cudaError_t dec_relayout_cross_kv(const __half* kv, __half* ck, __half* cv, int S, int S_pad, int d, int H, cudaStream_t s,
+                                  int64_t* n_launch);
 struct CtaStage;
 void dec_build_stage_table(const DecModel& hm, int ncta, std::vector<CtaStage>& tab);
 cudaError_t dec_launch_iteration_ring(const DecModel* dm, const DecHostInfo& hi, bool profile, cudaStream_t s);
