@@ -120,8 +120,8 @@ int64_t wm_last_launches(wm_handle* h, int32_t what);
  * the shared-memory weight ring (bulk-async prefetch across barriers; the product path).
  * Returns the previous mode. */
 int wm_set_decode_mode(wm_handle* h, int32_t mode);
-/* Engine options: "decode_mode" (as above); "enc_gemm" 0 = mma.sync encoder GEMM, 1 = tcgen05/TMA/TMEM
- * encoder GEMM. */
+/* Engine options: "decode_mode" (as above); "enc_gemm" 1 = tcgen05/TMA/TMEM encoder GEMM (default),
+ * 0 = mma.sync encoder GEMM (cross-check); "profile" 1 = record the stage timeline below. */
 int wm_set_option(wm_handle* h, const char* key, int32_t value);
 /* Debug: per-stage timeline of the last persistent iteration (after wm_set_option(h, "profile", 1)).
  * Rows of 24 int64: stage id, mode, layer; body ns and barrier-wait ns seen by the last CTA; then the

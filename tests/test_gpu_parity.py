@@ -121,6 +121,27 @@ def test_mel_encoder_logits_close(name, mode):
     assert np.abs(enc[::50] - g["enc_sample_fp32"]).max() < 3e-2
 
 
+@pytest.mark.parametrize("name", ["micro_linear_k4", "tiny_linear_k4"])
+def test_encoder_gemm_implementations_agree(name):
+    """The encoder GEMMs run on the tcgen05 / TMA / TMEM kernel by default; the mma.sync kernel
+    (option enc_gemm = 0) is the cross-check: same fp16 operands, fp32 accumulation in a different
+    order => the outputs agree to the fp16-rounding-flip level and both stay
+    within the oracle tolerance; the tokens are identical."""
+    g, cfg, seed, stream, kw = _load(name)
+    model, sd = _model(name)
+    pcm = synthetic_audio(float(g["audio_seconds"]), stream_id=stream)
+    outs, toks = [], []
+    for impl in (1, 0):
+        model.set_option("enc_gemm", impl)
+        toks.append(model.generate_from_pcm(pcm, **kw).cpu().numpy())
+        outs.append(model.encoder_output().numpy())
+    model.set_option("enc_gemm", 1)
+    assert np.abs(outs[0] - outs[1]).max() < 5e-3
+    for o in outs:
+        assert np.abs(o[::50] - g["enc_sample"]).max() < 5e-3
+    assert toks[0].tolist() == toks[1].tolist()
+
+
 def test_frontend_edge_cases():
     """Empty, very short and maximum-length clips (the extractor pads / truncates to 30 s)."""
     g, cfg, seed, stream, kw = _load("micro_linear_k4")

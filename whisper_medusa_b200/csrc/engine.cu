@@ -308,6 +308,7 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   }
   CK(enc_gemm_configure());
   h->tc_ok = (enc_gemm_tc_configure() == cudaSuccess);
+  h->enc_gemm_impl = h->tc_ok ? 1 : 0;   // tcgen05/TMA GEMM by default; option "enc_gemm" = 0 selects the mma.sync kernel
   (void)cudaGetLastError();
   // the skinny-GEMM work split assumes at most WM_MAXR(3) 16-row units per warp
   {
