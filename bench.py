@@ -39,6 +39,20 @@ import torch  # noqa: E402
 METRIC = "effective decoded tokens/sec (post-verify) Whisper-large-v2+Medusa"
 
 
+def ncu_traffic_bytes(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r1_ring_kernel_ncu.json) -- only meaningful for the configuration that
+    capture was taken on (large-v2, 10 linear heads, persistent mode); null otherwise."""
+    if not (args.preset == "large-v2" and args.heads == 10 and args.heads_type == "base_head" and args.mode == "persistent"):
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ring_kernel_ncu.json")) as f:
+            pl = json.load(f)["per_launch"]
+        return int(pl["dram_bytes_read"]) + int(pl["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(cfg, iterations: int, sweeps_a: int, n_mean: float):
     """fp16 bytes the decode loop must move, from the unit figures of SURVEY.md 8(d)
     (DESIGN.md section 4).  Returns (bytes of THIS engine's schedule, bytes of the reference schedule).
@@ -299,7 +313,7 @@ def main():
         "gpu_launches": int(allv[:, 6].sum()),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": ncu_traffic_bytes(args), "peak_source": peak_src,
                      "kernel": "dec_iteration_ring_kernel (one launch = one speculative iteration)"
                      if args.mode == "persistent" else f"decode iteration ({args.mode})",
                      "algorithmic_bytes_per_iteration": bytes_eng / max(1.0, it0), "ms_per_iteration": ms_iter,
