@@ -19,6 +19,12 @@
 
 namespace wm {
 
+__device__ __forceinline__ unsigned long long wm_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // -----------------------------------------------------------------------------------------
 // pass geometry (uniform across the grid; read from the loop state)
 // -----------------------------------------------------------------------------------------
@@ -348,7 +354,8 @@ __device__ __forceinline__ float dot64_h(const float* q, const uint4* kp) {
   }
   return s;
 }
-__device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
+__device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt,
+                                                unsigned long long* pr = nullptr) {
   const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
   const int d = m->d, H = m->H, T = g.T;
   const DecLayer& L = m->layers[layer];
@@ -369,6 +376,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
     for (int idx = tid; idx < rg * 64; idx += WM_DEC_THREADS)
       s_q[idx] = ldcg_f(&m->q[(size_t)(t0 + (idx >> 6)) * d + h * 64 + (idx & 63)]);
     cta_sync();
+    if (pr) pr[3] = wm_timer_ns();
     // scores (scaled by head_dim^-0.5; HF scales q, a power of two, so this is identical)
     const int npairs = rg * nk_max;
     for (int i0 = tid; i0 < npairs; i0 += WM_DEC_THREADS) {
@@ -381,6 +389,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
       s_p[r0 * WM_MAX_POS + j0] = ok0 ? dot64_h(s_q + r0 * 64, a) * 0.125f : -INFINITY;
     }
     cta_sync();
+    if (pr) pr[4] = wm_timer_ns();
     // softmax statistics: one warp per row
     for (int r = warp; r < rg; r += (WM_DEC_THREADS >> 5)) {
       const int nk = g.base + t0 + r + 1;
@@ -394,6 +403,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
       if (lane == 0) s_st[r] = sum;
     }
     cta_sync();
+    if (pr) pr[5] = wm_timer_ns();
     // P * V : thread = (row r, key group kg, dim group dg of 8 dims)
     {
       const int KG = (WM_DEC_THREADS / 8) / rg;
@@ -421,6 +431,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
 #pragma unroll
       for (int e = 0; e < 8; ++e) s_acc[gI * 64 + dg * 8 + e] = a[e];
       cta_sync();
+      if (pr) pr[6] = wm_timer_ns();
       if (tid < rg * 64) {
         const int rr = tid >> 6, c = tid & 63;
         float o = 0.f;
@@ -438,8 +449,9 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
 // -----------------------------------------------------------------------------------------
 #define WM_CH_MAX 216   // keys per chunk (S = 1500 over >= 7 chunks)
 #define WM_CH_PAD 224   // rounded up to the MMA k-step (16 keys)
+#define WM_SS_STRIDE (WM_CH_PAD + 8)   // score row stride in floats: 32 B (mod 128) => conflict-free 8-byte fragment loads
 __host__ __device__ constexpr size_t cross_attn_smem_bytes() {
-  return (size_t)2 * WM_CH_PAD * 72 * sizeof(__half) + (size_t)WM_MAX_T * WM_CH_PAD * sizeof(float) +
+  return (size_t)2 * WM_CH_PAD * 72 * sizeof(__half) + (size_t)WM_MAX_T * WM_SS_STRIDE * sizeof(float) +
          (size_t)2 * 16 * 72 * sizeof(__half) + (size_t)2 * WM_MAX_T * sizeof(float);   // K, V chunk + cross_scratch_bytes()
 }
 __device__ __forceinline__ void split_hilo(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -456,26 +468,60 @@ __device__ __forceinline__ void split_hilo(float a, float b, uint32_t& hi, uint3
 // zero) sit in shared memory -- in the scratch area (stage kernels) or in two ring slots (ring kernel).
 // `after_qk` / `after_pv` run once the last read of sK / sV is over (the ring hands the slots back there).
 struct CrossScratch {
-  float* sS;      // [16][CH_PAD] scores, then probabilities
+  float* sS;      // [16][WM_SS_STRIDE] scores, then the probabilities as fp16 {hi2, lo2} key pairs (in place)
   __half* sQh;    // [16][72]
   __half* sQl;
   float* sM;      // [16] max, [16] sum
 };
 __host__ __device__ constexpr size_t cross_scratch_bytes() {
-  return (size_t)WM_MAX_T * WM_CH_PAD * sizeof(float) + (size_t)2 * 16 * 72 * sizeof(__half) + (size_t)2 * WM_MAX_T * sizeof(float);
+  return (size_t)WM_MAX_T * WM_SS_STRIDE * sizeof(float) + (size_t)2 * 16 * 72 * sizeof(__half) + (size_t)2 * WM_MAX_T * sizeof(float);
 }
 __device__ __forceinline__ CrossScratch cross_scratch(unsigned char* p) {
   CrossScratch cs;
   cs.sS = reinterpret_cast<float*>(p);
-  cs.sQh = reinterpret_cast<__half*>(cs.sS + WM_MAX_T * WM_CH_PAD);
+  cs.sQh = reinterpret_cast<__half*>(cs.sS + WM_MAX_T * WM_SS_STRIDE);
   cs.sQl = cs.sQh + 16 * 72;
   cs.sM = reinterpret_cast<float*>(cs.sQl + 16 * 72);
   return cs;
 }
+// combine the chunk partials of head h (run by the CTA that arrives last for the head): warp per query row,
+// lane = output dims (lane, lane + 32); the chunk statistics sit one per lane and are broadcast by shuffles.
+// Every load is in flight before the first use (a loop with a run-time bound would pay one L2 round trip per
+// chunk); chunks are combined in chunk order => deterministic.
+__device__ __forceinline__ void cross_attn_fold(const DecModel* m, int T, int h, int nch) {
+  const int d = m->d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (WM_DEC_THREADS >> 5);
+  const size_t cstride = (size_t)WM_MAX_T * (WM_HEAD_DIM + 2);
+  for (int rr = warp; rr < T; rr += nwarps) {
+    const float* base = m->cross_part + ((size_t)h * WM_CROSS_CHUNKS * WM_MAX_T + rr) * (WM_HEAD_DIM + 2);
+    float mm = -INFINITY, ll = 0.f;
+    if (lane < nch) { mm = __ldcg(base + lane * cstride + 64); ll = __ldcg(base + lane * cstride + 65); }
+    float v0[WM_CROSS_CHUNKS], v1[WM_CROSS_CHUNKS];
+#pragma unroll
+    for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc)
+      if (cc < nch) { v0[cc] = __ldcg(base + cc * cstride + lane); v1[cc] = __ldcg(base + cc * cstride + 32 + lane); }
+    const float M = warp_max(mm);
+    const float wl = (lane < nch) ? expf(mm - M) : 0.f;
+    float num0 = 0.f, num1 = 0.f, den = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc)
+      if (cc < nch) {
+        const float w = __shfl_sync(0xffffffffu, wl, cc);
+        const float l = __shfl_sync(0xffffffffu, ll, cc);
+        num0 = fmaf(w, v0[cc], num0);
+        num1 = fmaf(w, v1[cc], num1);
+        den = fmaf(w, l, den);
+      }
+    float* o = m->attn + (size_t)rr * d + h * 64;
+    o[lane] = num0 / den;
+    o[32 + lane] = num1 / den;
+  }
+}
+
 template <class AfterQK, class AfterPV>
 __device__ __forceinline__ void cross_attn_core(const DecModel* m, int T, int h, int c, int nch, int nk, int nk_pad,
                                                 const __half* sK, const __half* sV, const CrossScratch& cs,
-                                                AfterQK&& after_qk, AfterPV&& after_pv) {
+                                                AfterQK&& after_qk, AfterPV&& after_pv, unsigned long long* pr = nullptr) {
   __shared__ int s_last;
   float* sS = cs.sS; __half* sQh = cs.sQh; __half* sQl = cs.sQl; float* sM = cs.sM;
   const int d = m->d;
@@ -492,6 +538,7 @@ __device__ __forceinline__ void cross_attn_core(const DecModel* m, int T, int h,
     *reinterpret_cast<uint32_t*>(sQl + r * 72 + c2) = lo;
   }
   cta_sync();
+  if (pr) pr[4] = wm_timer_ns();
   // ---- S = Q K^T * head_dim^-0.5 : warp w takes key tiles (8 keys) w, w + nwarps, ... ----
   {
     uint32_t qh[4][4], ql[4][4];
@@ -513,52 +560,62 @@ __device__ __forceinline__ void cross_attn_core(const DecModel* m, int T, int h,
         mma_16816(acc, qh[2 * k2 + 1][0], qh[2 * k2 + 1][1], qh[2 * k2 + 1][2], qh[2 * k2 + 1][3], b2, b3);
         mma_16816(acc, ql[2 * k2 + 1][0], ql[2 * k2 + 1][1], ql[2 * k2 + 1][2], ql[2 * k2 + 1][3], b2, b3);
       }
-      float* s0 = sS + gq * WM_CH_PAD + nt * 8 + 2 * tq;
-      s0[0] = acc[0] * 0.125f; s0[1] = acc[1] * 0.125f;
-      s0[8 * WM_CH_PAD] = acc[2] * 0.125f; s0[8 * WM_CH_PAD + 1] = acc[3] * 0.125f;
+      float* s0 = sS + gq * WM_SS_STRIDE + nt * 8 + 2 * tq;
+      *reinterpret_cast<float2*>(s0) = make_float2(acc[0] * 0.125f, acc[1] * 0.125f);
+      *reinterpret_cast<float2*>(s0 + 8 * WM_SS_STRIDE) = make_float2(acc[2] * 0.125f, acc[3] * 0.125f);
     }
   }
   cta_sync();
+  if (pr) pr[5] = wm_timer_ns();
   after_qk();
-  // ---- per-row max / exp / sum : warp per row; rows >= T and keys >= nk become zero probability ----
+  // ---- per-row max / exp / sum : warp per row, two keys per lane; rows >= T and keys >= nk become zero
+  // probability.  The probabilities replace the scores IN PLACE as the fp16 operand pairs of the P V MMAs:
+  // floats (p[2j], p[2j+1]) -> { half2 hi, half2 lo }, so the 8 warps of the next phase do not each redo the split.
   for (int r = warp; r < 16; r += nwarps) {
-    float* p = sS + r * WM_CH_PAD;
+    float* p = sS + r * WM_SS_STRIDE;
     if (r < T) {
       float mx = -INFINITY;
-      for (int jj = lane; jj < nk; jj += 32) mx = fmaxf(mx, p[jj]);
+      for (int pj = lane; 2 * pj < nk; pj += 32) {
+        const float2 v = *reinterpret_cast<const float2*>(p + 2 * pj);
+        mx = fmaxf(mx, v.x);
+        if (2 * pj + 1 < nk) mx = fmaxf(mx, v.y);
+      }
       mx = warp_max(mx);
       float sum = 0.f;
-      for (int jj = lane; jj < nk_pad; jj += 32) {
-        const float e = (jj < nk) ? expf(p[jj] - mx) : 0.f;
-        p[jj] = e;
-        sum += e;
+      for (int pj = lane; 2 * pj < nk_pad; pj += 32) {
+        const float2 v = *reinterpret_cast<const float2*>(p + 2 * pj);
+        const float e0 = (2 * pj < nk) ? expf(v.x - mx) : 0.f;
+        const float e1 = (2 * pj + 1 < nk) ? expf(v.y - mx) : 0.f;
+        uint2 o;
+        split_hilo(e0, e1, o.x, o.y);
+        *reinterpret_cast<uint2*>(p + 2 * pj) = o;
+        sum += e0 + e1;
       }
       sum = warp_sum(sum);
       if (lane == 0) { sM[r] = mx; sM[WM_MAX_T + r] = sum; }
     } else {
-      for (int jj = lane; jj < nk_pad; jj += 32) p[jj] = 0.f;
+      for (int pj = lane; 2 * pj < nk_pad; pj += 32) *reinterpret_cast<uint2*>(p + 2 * pj) = make_uint2(0u, 0u);
     }
   }
   cta_sync();
+  if (pr) pr[6] = wm_timer_ns();
   // ---- O = P V : warp w < 8 owns output dims w*8 .. w*8+7, all key steps ----
   if (warp < 8) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acl[4] = {0.f, 0.f, 0.f, 0.f};
     for (int ks = 0; ks < nk_pad / 16; ++ks) {
-      const float* p0 = sS + gq * WM_CH_PAD + ks * 16 + 2 * tq;
-      const float2 a00 = *reinterpret_cast<const float2*>(p0);
-      const float2 a10 = *reinterpret_cast<const float2*>(p0 + 8 * WM_CH_PAD);
-      const float2 a01 = *reinterpret_cast<const float2*>(p0 + 8);
-      const float2 a11 = *reinterpret_cast<const float2*>(p0 + 8 * WM_CH_PAD + 8);
-      uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-      split_hilo(a00.x, a00.y, h0, l0);   // row g,   keys 2t..2t+1
-      split_hilo(a10.x, a10.y, h1, l1);   // row g+8
-      split_hilo(a01.x, a01.y, h2, l2);   // row g,   keys 2t+8..
-      split_hilo(a11.x, a11.y, h3, l3);   // row g+8
+      const float* p0 = sS + gq * WM_SS_STRIDE + ks * 16 + 2 * tq;
+      const uint2 a00 = *reinterpret_cast<const uint2*>(p0);                          // row g,   keys 2t..2t+1  {hi, lo}
+      const uint2 a10 = *reinterpret_cast<const uint2*>(p0 + 8 * WM_SS_STRIDE);      // row g+8
+      const uint2 a01 = *reinterpret_cast<const uint2*>(p0 + 8);                      // row g,   keys 2t+8..
+      const uint2 a11 = *reinterpret_cast<const uint2*>(p0 + 8 * WM_SS_STRIDE + 8);  // row g+8
       uint32_t b0, b1;
       ldmatrix_x2_trans(b0, b1, sV + (ks * 16 + (lane & 15)) * 72 + warp * 8);
-      mma_16816(acc, h0, h1, h2, h3, b0, b1);
-      mma_16816(acc, l0, l1, l2, l3, b0, b1);
+      mma_16816(acc, a00.x, a10.x, a01.x, a11.x, b0, b1);
+      mma_16816(acl, a00.y, a10.y, a01.y, a11.y, b0, b1);
     }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] += acl[e];
     float* out0 = m->cross_part + ((size_t)(h * WM_CROSS_CHUNKS + c) * WM_MAX_T + gq) * (WM_HEAD_DIM + 2) + warp * 8 + 2 * tq;
     if (gq < T) { out0[0] = acc[0]; out0[1] = acc[1]; }
     if (gq + 8 < T) { out0[8 * (WM_HEAD_DIM + 2)] = acc[2]; out0[8 * (WM_HEAD_DIM + 2) + 1] = acc[3]; }
@@ -571,6 +628,7 @@ __device__ __forceinline__ void cross_attn_core(const DecModel* m, int T, int h,
   // fold: the chunk that arrives last for this head (always in chunk order => deterministic)
   // (release-only arrival; the partials are read back with L2-coherent loads, see common.cuh)
   cta_sync();
+  if (pr) pr[7] = wm_timer_ns();
   after_pv();
   if (tid == 0) {
     const unsigned int prev = atom_add_release(&m->cross_cnt[h], 1u);
@@ -578,35 +636,11 @@ __device__ __forceinline__ void cross_attn_core(const DecModel* m, int T, int h,
     if (s_last) m->cross_cnt[h] = 0u;   // everybody has arrived: re-arm for the next layer
   }
   cta_sync();
+  if (pr) pr[8] = wm_timer_ns();
   if (s_last) {
-    const size_t cstride = (size_t)WM_MAX_T * (WM_HEAD_DIM + 2);
-    for (int idx = tid; idx < T * 64; idx += WM_DEC_THREADS) {
-      const int rr = idx >> 6, e = idx & 63;
-      const float* base = m->cross_part + ((size_t)h * WM_CROSS_CHUNKS * WM_MAX_T + rr) * (WM_HEAD_DIM + 2);
-      // every load of the element in flight at once (a loop with a run-time bound would pay one L2 round trip per chunk)
-      float mv[WM_CROSS_CHUNKS], lv[WM_CROSS_CHUNKS], vv[WM_CROSS_CHUNKS];
-#pragma unroll
-      for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc)
-        if (cc < nch) {
-          mv[cc] = __ldcg(base + cc * cstride + 64);
-          lv[cc] = __ldcg(base + cc * cstride + 65);
-          vv[cc] = __ldcg(base + cc * cstride + e);
-        }
-      float M = -INFINITY;
-#pragma unroll
-      for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc)
-        if (cc < nch) M = fmaxf(M, mv[cc]);
-      float num = 0.f, den = 0.f;
-#pragma unroll
-      for (int cc = 0; cc < WM_CROSS_CHUNKS; ++cc)
-        if (cc < nch) {
-          const float w = expf(mv[cc] - M);
-          num = fmaf(w, vv[cc], num);
-          den = fmaf(w, lv[cc], den);
-        }
-      m->attn[(size_t)rr * d + h * 64 + e] = num / den;
-    }
+    cross_attn_fold(m, T, h, nch);
   }
+  if (pr) { pr[10] = wm_timer_ns(); pr[11] = s_last ? 1000ull : 0ull; }
 }
 
 __device__ __forceinline__ void stage_cross_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt) {
@@ -1052,10 +1086,10 @@ __host__ __device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mo
 // that kernel's code
 template <bool WITH_GEMM = true>
 __device__ void run_stage(const DecModel* m, int stage, int mode, int layer, int cta, int ncta, unsigned char* smem,
-                          const PassGeom* gopt = nullptr) {
+                          const PassGeom* gopt = nullptr, unsigned long long* pr = nullptr) {
   switch (stage) {
     case ST_EMBED: stage_embed(m, mode, cta, ncta, gopt); break;
-    case ST_SELF_ATTN: stage_self_attn(m, mode, layer, cta, ncta, smem, gopt); break;
+    case ST_SELF_ATTN: stage_self_attn(m, mode, layer, cta, ncta, smem, gopt, pr); break;
     case ST_CROSS_ATTN: stage_cross_attn(m, mode, layer, cta, ncta, smem, gopt); break;
     case ST_FINAL_LN: stage_final_ln(m, mode, cta, ncta, gopt); break;
     case ST_COPY_HIDDEN: stage_copy_hidden_to_x(m, mode, cta, ncta, gopt); break;

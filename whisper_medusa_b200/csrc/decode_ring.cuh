@@ -464,7 +464,8 @@ __device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* sm
 // read them in place (the cache rows already have the 72-half shared-memory stride).
 // ---------------------------------------------------------------------------------------------
 template <int D>
-__device__ __forceinline__ void stage_cross_attn_ring(RingState& rs, unsigned char* smem, const DecModel* m, int T, int cta, int ncta) {
+__device__ __forceinline__ void stage_cross_attn_ring(RingState& rs, unsigned char* smem, const DecModel* m, int T, int cta, int ncta,
+                                                      unsigned long long* pr) {
   using G = RingGeom<D>;
   uint64_t* const full = reinterpret_cast<uint64_t*>(smem + G::BAR_OFF);
   uint64_t* const empty = full + WM_RING_G;
@@ -487,6 +488,7 @@ __device__ __forceinline__ void stage_cross_attn_ring(RingState& rs, unsigned ch
     __half* sV = reinterpret_cast<__half*>(smem + (size_t)slot_v * G::SLOT_BYTES);
     while (!mbar_try_wait(full + slot_k, par_k)) { }
     while (!mbar_try_wait(full + slot_v, par_v)) { }
+    if (pr) pr[3] = global_timer_ns();
     // rows nk .. nk_pad read as zero (their probabilities are zero, but 0 * stale bits could be NaN)
     for (int idx = tid; idx < (nk_pad - nk) * 9; idx += WM_DEC_THREADS) {
       reinterpret_cast<uint4*>(sK)[nk * 9 + idx] = make_uint4(0, 0, 0, 0);
@@ -495,7 +497,7 @@ __device__ __forceinline__ void stage_cross_attn_ring(RingState& rs, unsigned ch
     cross_attn_core(
         m, T, h, c, nch, nk, nk_pad, sK, sV, cs,
         [&] { if (tid == 0) mbar_arrive(empty + slot_k); },
-        [&] { if (tid == 0) mbar_arrive(empty + slot_v); });
+        [&] { if (tid == 0) mbar_arrive(empty + slot_v); }, pr);
   }
 }
 
@@ -571,9 +573,9 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
     if (is_gemm_stage(stage)) {
       stage_gemm_ring<D>(rs, smem, m, sd, pgv.T, pgv.base, pr);
     } else if (stage == ST_CROSS_ATTN) {
-      stage_cross_attn_ring<D>(rs, smem, m, pgv.T, cta, ncta);
+      stage_cross_attn_ring<D>(rs, smem, m, pgv.T, cta, ncta, pr);
     } else {
-      run_stage<false>(m, stage, mode, sd->layer, cta, ncta, smem + G::SCRATCH_OFF, &pgv);
+      run_stage<false>(m, stage, mode, sd->layer, cta, ncta, smem + G::SCRATCH_OFF, &pgv, pr);
     }
     if (prof) pr[15] = global_timer_ns();
     if (fetch) reinterpret_cast<uint32_t*>(&s_desc[(ip + 1) & 1])[lane] = nxt_w;
