@@ -34,7 +34,7 @@ CASES = {
     "tiny_linear_k4": ("tiny.en", 4, "base_head", 3, 5.0, 0, 200, None, 1.0),
     "tiny_block_k4": ("tiny.en", 4, "medusa_block", 1, 5.0, 0, 200, None, 1.0),
     "large_linear_k10": ("large-v2", 10, "base_head", 0, 30.0, 0, 448, None, 1.0),
-    "large_block_k10": ("large-v2", 10, "medusa_block", 0, 30.0, 0, 448, None, 1.0),
+    "large_block_k10": ("large-v2", 10, "medusa_block", 0, 30.0, 0, 120, None, 1.0),   # short budget: ~10 iterations
 }
 
 TOPN = 16

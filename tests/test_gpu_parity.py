@@ -207,3 +207,17 @@ def test_large_v2_tokens_bit_exact_vs_golden(mode):
             lg = model.last_logits(which).numpy()
             assert _rel_err(lg, ref.numpy()) < 1e-3, ab
             assert _rel_err(lg[:, ::97], g[f"logits{ab}0_strided"]) < 5e-3, ab
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(GOLDEN, "large_block_k10.npz")), reason="fixture missing")
+@pytest.mark.parametrize("mode", ["persistent", "graph"])
+def test_large_v2_block_heads_tokens_bit_exact_vs_golden(mode):
+    """whisper-large-v2 + the Medusa-Block head type (one extra decoder layer feeding 10 heads; reference
+    model.py:1285-1301), short token budget."""
+    g, cfg, seed, stream, kw = _load("large_block_k10")
+    model, sd = _model("large_block_k10")
+    model.set_decode_mode(mode)
+    pcm = synthetic_audio(float(g["audio_seconds"]), stream_id=stream)
+    out = model.generate_from_pcm(pcm, **kw)[0].tolist()
+    assert out == g["tokens"].tolist()
+    assert model.last_trace.accept_lengths == g["accept_lengths"].tolist()

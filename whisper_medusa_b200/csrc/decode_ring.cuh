@@ -50,6 +50,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -271,13 +274,6 @@ __device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* sm
     // this CTA's bias slice of the NEXT GEMM stage -> L2 (biases are cold: 2 GB of weights pass through L2 per iteration)
     if (lane < sd->pf_bias_lines) prefetch_l2(reinterpret_cast<const unsigned char*>(sd->pf_bias) + (size_t)lane * 128);
   }
-  // output element owned by this thread in the fold below
-  const int e_ = tid >> 5;
-  const int j_ = (e_ >> 2) & 1, i_ = e_ & 3;
-  const int token = gq + ((i_ >= 2) ? 8 : 0);
-  const int rloc = j_ * 8 + 2 * tq + (i_ & 1);
-  const bool mine = tid < 256 && token < T;
-
   while (!mbar_try_wait(xbar, rs.xpar)) { }
   rs.xpar ^= 1u;
   if (pr) pr[8] = global_timer_ns();
@@ -334,19 +330,16 @@ __device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* sm
   const bool ksplit = sd->segs > 1;
   const int epi = sd->epi;
   const int n_begin = sd->n_begin;
-  for (int u = 0; u < units; ++u) {
-    const int nvalid = min(16, n_rows - u * 16);
-    // this thread's bias and (residual epilogue) old value: L2 hits that complete while the MMAs run
-    float bias_v = 0.f, old = 0.f;
-    if (mine && rloc < nvalid && !ksplit) {
-      const float* bias = sd->bias;
-      if (bias) bias_v = bias[n_begin + u * 16 + rloc];
-      if (epi == EPI_RESID) old = ldcg_f(&sd->out[(size_t)token * sd->ldo + n_begin + u * 16 + rloc]);
-    }
-    if (pr && u == 0) { pr[12] = mbar_try_wait(full + rs.slot, rs.par) ? 1000ull : 0ull; pr[13] = global_timer_ns(); }
-    while (!mbar_try_wait(full + rs.slot, rs.par)) { }
-    if (pr && u == 0) pr[4] = global_timer_ns();
-    if (warp < G::NKS) {
+  // ---- unit loop, warp-specialised: warps 0..NKS-1 run the MMAs of unit u while the remaining warps finish unit
+  // u-1 (k-slice reduction, bias, epilogue, global stores).  Named barrier 2 = "partials of unit u written",
+  // named barrier 3 = "partials of unit u read" (the partial buffer is single: its rewrite waits for the readers).
+  constexpr int NE = WM_DEC_THREADS - G::NKS * 32;   // epilogue threads
+  if (warp < G::NKS) {
+    for (int u = 0; u < units; ++u) {
+      const int nvalid = min(16, n_rows - u * 16);
+      if (pr && u == 0) { pr[12] = mbar_try_wait(full + rs.slot, rs.par) ? 1000ull : 0ull; pr[13] = global_timer_ns(); }
+      while (!mbar_try_wait(full + rs.slot, rs.par)) { }
+      if (pr && u == 0) pr[4] = global_timer_ns();
       const __half* sl = reinterpret_cast<const __half*>(smem + (size_t)rs.slot * G::SLOT_BYTES);
       const bool v0 = gq < nvalid, v1 = (gq + 8) < nvalid;
       const __half* w0p = sl + (size_t)gq * (G::ROW_STRIDE / 2) + warp * G::KS + 8 * tq;
@@ -376,49 +369,86 @@ __device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* sm
         mma_16816(c1h, p1.x, q1.x, p1.z, q1.z, wb.z, wb.w);
         mma_16816(c1l, p1.y, q1.y, p1.w, q1.w, wb.z, wb.w);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + rs.slot);   // this warp is done with the slot (the barrier counts NKS arrivals)
+      if (++rs.slot == WM_RING_G) { rs.slot = 0; rs.par ^= 1u; }
+      if (pr && u == 0) pr[5] = global_timer_ns();
+      if (u > 0) asm volatile("bar.sync 3, %0;" ::"n"(WM_DEC_THREADS) : "memory");   // partials of unit u-1 have been read
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         partial[warp * 256 + e * 32 + lane] = c0h[e] + c0l[e];
         partial[warp * 256 + (4 + e) * 32 + lane] = c1h[e] + c1l[e];
       }
+      asm volatile("bar.arrive 2, %0;" ::"n"(WM_DEC_THREADS) : "memory");
+      if (pr && u == 0) pr[6] = global_timer_ns();
     }
-    cta_sync();   // partials visible; every read of the slot is done
-    if (pr && u == 0) pr[5] = global_timer_ns();
-    if (tid == 0) mbar_arrive(empty + rs.slot);   // hand the slot back to the producer
-    if (++rs.slot == WM_RING_G) { rs.slot = 0; rs.par ^= 1u; }
-    if (mine && rloc < nvalid) {
-      float s = 0.f;
+  } else {
+    const int etid = tid - G::NKS * 32;
+    constexpr int NOUT = (256 + NE - 1) / NE;   // outputs per epilogue thread and unit
+    for (int u = 0; u < units; ++u) {
+      const int nvalid = min(16, n_rows - u * 16);
+      // this thread's outputs of the unit; their bias / residual loads are in flight while the MMA warps work
+      float bias_v[NOUT], old[NOUT];
 #pragma unroll
-      for (int ks = 0; ks < G::NKS; ++ks) s += partial[ks * 256 + tid];
-      const int row = n_begin + u * 16 + rloc;
+      for (int k = 0; k < NOUT; ++k) {
+        const int o = etid + k * NE, token = o >> 4, rloc = o & 15;
+        bias_v[k] = 0.f; old[k] = 0.f;
+        if (o < 256 && token < T && rloc < nvalid && !ksplit) {
+          const float* bias = sd->bias;
+          if (bias) bias_v[k] = bias[n_begin + u * 16 + rloc];
+          if (epi == EPI_RESID) old[k] = ldcg_f(&sd->out[(size_t)token * sd->ldo + n_begin + u * 16 + rloc]);
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(WM_DEC_THREADS) : "memory");   // partials of unit u are written
+      float sum[NOUT];
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) {
+        const int o = etid + k * NE, token = o >> 4, rloc = o & 15;
+        sum[k] = 0.f;
+        if (o < 256 && token < T && rloc < nvalid) {
+          // where the MMA fragment layout put (token, rloc): accumulator (j = n8 tile, i = register) of lane (g, t)
+          const int idx = (((rloc >> 3) * 4) + ((token >= 8) ? 2 : 0) + (rloc & 1)) * 32 + (token & 7) * 4 + ((rloc & 7) >> 1);
+#pragma unroll
+          for (int ks = 0; ks < G::NKS; ++ks) sum[k] += partial[ks * 256 + idx];
+        }
+      }
+      if (u + 1 < units) asm volatile("bar.arrive 3, %0;" ::"n"(WM_DEC_THREADS) : "memory");
       float* out = sd->out;
       const int ldo = sd->ldo;
-      // common epilogues inline (bias was fetched while the MMAs ran); the Medusa-head ones are rare
-      if (ksplit) {
-        m->gemm_part[((size_t)sd->seg * 16 + token) * sd->N + row] = s;
-      } else if (epi == EPI_RESID) {
-        out[(size_t)token * ldo + row] = old + (s + bias_v);
-      } else if (epi == EPI_STORE || epi == EPI_LOGITS) {
-        out[(size_t)token * ldo + row] = s + bias_v;
-      } else if (epi == EPI_GELU) {
-        out[(size_t)token * ldo + row] = gelu_erf(s + bias_v);
-      } else if (epi == EPI_QKV) {
-        const float v = s + bias_v;
-        const DecLayer& L = m->layers[sd->layer];
-        if (row < D) out[(size_t)token * ldo + row] = v;
-        else if (row < 2 * D) L.self_k[(size_t)(base + token) * D + (row - D)] = __float2half_rn(v);
-        else L.self_v[(size_t)(base + token) * D + (row - 2 * D)] = __float2half_rn(v);
-      } else if (epi == EPI_HEADS_A) {
-        // head `row / d` on the newest token's hidden state: x + SiLU(W x + b)  (medusa ResBlock)
-        const int head = row / D, n = row - head * D;
-        out[(size_t)(sd->out_row0 + head) * ldo + n] = xbuf_value(xb, G::XS, 0, n) + silu(s + bias_v);
-      } else {   // EPI_HEAD_B
-        out[(size_t)token * ldo + row] = xbuf_value(xb, G::XS, token, row) + silu(s + bias_v);
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) {
+        const int o = etid + k * NE, token = o >> 4, rloc = o & 15;
+        if (!(o < 256 && token < T && rloc < nvalid)) continue;
+        const int row = n_begin + u * 16 + rloc;
+        const float s = sum[k];
+        // common epilogues inline; the Medusa-head ones are rare
+        if (ksplit) {
+          m->gemm_part[((size_t)sd->seg * 16 + token) * sd->N + row] = s;
+        } else if (epi == EPI_RESID) {
+          out[(size_t)token * ldo + row] = old[k] + (s + bias_v[k]);
+        } else if (epi == EPI_STORE || epi == EPI_LOGITS) {
+          out[(size_t)token * ldo + row] = s + bias_v[k];
+        } else if (epi == EPI_GELU) {
+          out[(size_t)token * ldo + row] = gelu_erf(s + bias_v[k]);
+        } else if (epi == EPI_QKV) {
+          const float v = s + bias_v[k];
+          const DecLayer& L = m->layers[sd->layer];
+          if (row < D) out[(size_t)token * ldo + row] = v;
+          else if (row < 2 * D) L.self_k[(size_t)(base + token) * D + (row - D)] = __float2half_rn(v);
+          else L.self_v[(size_t)(base + token) * D + (row - 2 * D)] = __float2half_rn(v);
+        } else if (epi == EPI_HEADS_A) {
+          // head `row / d` on the newest token's hidden state: x + SiLU(W x + b)  (medusa ResBlock)
+          const int head = row / D, n = row - head * D;
+          out[(size_t)(sd->out_row0 + head) * ldo + n] = xbuf_value(xb, G::XS, 0, n) + silu(s + bias_v[k]);
+        } else {   // EPI_HEAD_B
+          out[(size_t)token * ldo + row] = xbuf_value(xb, G::XS, token, row) + silu(s + bias_v[k]);
+        }
       }
     }
-    cta_sync();   // partial buffer reusable
-    if (pr && u == 0) pr[6] = global_timer_ns();
+    for (int u = 0; u < units; ++u)
+      if (++rs.slot == WM_RING_G) { rs.slot = 0; rs.par ^= 1u; }   // keep the (uniform) ring state in step with the MMA warps
   }
+  cta_sync();   // every store of the stage issued; partial buffer and X buffer free
   if (pr) pr[14] = global_timer_ns();
   if (ksplit) {
     // the last of the `segs` CTAs of this row block folds the segment partials, always in segment order
@@ -496,8 +526,8 @@ __device__ __forceinline__ void stage_cross_attn_ring(RingState& rs, unsigned ch
     }
     cross_attn_core(
         m, T, h, c, nch, nk, nk_pad, sK, sV, cs,
-        [&] { if (tid == 0) mbar_arrive(empty + slot_k); },
-        [&] { if (tid == 0) mbar_arrive(empty + slot_v); }, pr);
+        [&] { if (tid == 0) mbar_arrive_n(empty + slot_k, G::NKS); },
+        [&] { if (tid == 0) mbar_arrive_n(empty + slot_v, G::NKS); }, pr);
   }
 }
 
@@ -518,7 +548,7 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
   uint64_t* const xbar = empty + WM_RING_G;
   uint64_t* const pbar = xbar + 1;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WM_RING_G; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < WM_RING_G; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, G::NKS); }   // a slot is released by every MMA warp
     mbar_init(xbar, 1);
     mbar_init(pbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
