@@ -69,9 +69,17 @@ def main():
     order = [7, 8, 9, 10, 3, 13, 4, 5, 6, 14, 15, 1, 2]
     names = ["desc", "x-land", "ln-stat", "split", "staged", "pre-w", "w-ok", "mma", "epi", "units", "fn-end", "body", "barrier"]
     agg = OrderedDict()
+    agg2 = OrderedDict()
+    gemm = {"QKV", "OPROJ", "CROSS_Q", "CROSS_O", "FC1", "FC2", "HEADS", "VOCAB"}
     for row in rows:
         st, mode, layer, bN, wN = row[:5]
         raw = row[5:21]
+        if STAGES[st] not in gemm:
+            b = agg2.setdefault((STAGES[st], MODES[mode]), np.zeros(12))
+            b[0] += 1
+            for k in range(8):
+                b[1 + k] += max(raw[3 + k], 0)
+            b[9] += max(raw[1], 0); b[10] += max(raw[2], 0); b[11] += raw[11]
         a = agg.setdefault((STAGES[st], MODES[mode]), np.zeros(3 + len(order) + 2))
         a[0] += 1; a[1] += bN; a[2] += wN
         for k, idx in enumerate(order):
@@ -88,6 +96,12 @@ def main():
         print(f"{st:<12}{mode:<5}{int(cnt):>3}" + "".join(f"{a[3 + k] / cnt / 1e3:>8.2f}" for k in range(len(order)))
               + f"{a[1] / cnt / 1e3:>8.2f}{a[2] / cnt / 1e3:>8.2f}  {a[3 + len(order)] / cnt / 1e3:>7.2f} {a[4 + len(order)] / cnt / 1e3:>6.2f}")
     print(f"sum over stages of the last iteration (CTA 0): {tot / 1e3:.3f} ms")
+    # raw probe offsets (us from stage begin, CTA 0) of the non-GEMM stages: pr[3..10], body end, barrier end
+    print("raw probes of the attention / select stages (us): p3 p4 p5 p6 p7 p8 p9 p10 | body barrier | flag11")
+    for (st, mode), a in agg2.items():
+        cnt = a[0]
+        print(f"{st:<12}{mode:<5}{int(cnt):>3}" + "".join(f"{a[1 + k] / cnt / 1e3:>8.2f}" for k in range(8))
+              + f" |{a[9] / cnt / 1e3:>8.2f}{a[10] / cnt / 1e3:>8.2f} |{a[11] / cnt / 1e3:>6.2f}")
     model.close()
 
 

@@ -44,7 +44,9 @@ struct alignas(16) CtaStage {
   const float* nx_g;        // LayerNorm vectors of the NEXT instruction (null: it has none)
   const float* nx_b;
   const float* pf_bias;     // this CTA's bias slice of the next GEMM stage (L2 prefetch)
-  int pad_[4];
+  int presplit;             // 1: X was written by its producer in the fp16 hi/lo operand format (no split pass)
+  int out_split;            // 1: the epilogue writes `out` in that format (the consumer is a presplit stage)
+  int pad_[2];
 };
 static_assert(sizeof(CtaStage) == 128, "CtaStage must be one 128-byte line");
 
@@ -98,6 +100,14 @@ __device__ __forceinline__ int ldcg_i(const int* p) { return __ldcg(p); }
 __device__ __forceinline__ float2 ldcg_f2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
 __device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ uint4 ldcg_u4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+// Activation element (row base `row`, column n) in the fp16 hi/lo operand format of the ring kernel's GEMM stages:
+// every float pair (k, k+1) occupies its 8 bytes as { half2 hi(k,k+1), half2 lo(k,k+1) } (decode_ring.cuh).
+__device__ __forceinline__ void store_split(float* row, int n, float v) {
+  __half* p = reinterpret_cast<__half*>(row) + (size_t)(n >> 1) * 4 + (n & 1);
+  const __half h = __float2half_rn(v);
+  p[0] = h;
+  p[2] = __float2half_rn(v - __half2float(h));
+}
 __device__ __forceinline__ void red_add_release(unsigned int* p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

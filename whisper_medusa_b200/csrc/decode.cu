@@ -354,6 +354,7 @@ __device__ __forceinline__ float dot64_h(const float* q, const uint4* kp) {
   }
   return s;
 }
+template <bool SPLIT_OUT = false>
 __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int layer, int cta, int ncta, unsigned char* smem_raw, const PassGeom* gopt,
                                                 unsigned long long* pr = nullptr) {
   const PassGeom g = gopt ? *gopt : pass_geom(m, mode);
@@ -436,7 +437,8 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
         const int rr = tid >> 6, c = tid & 63;
         float o = 0.f;
         for (int k2 = 0; k2 < KG; ++k2) o += s_acc[(rr * KG + k2) * 64 + c];
-        m->attn[(size_t)(t0 + rr) * d + h * 64 + c] = o / s_st[rr];
+        if (SPLIT_OUT) store_split(m->attn + (size_t)(t0 + rr) * d, h * 64 + c, o / s_st[rr]);   // (ring kernel: operand format of the O-projection)
+        else m->attn[(size_t)(t0 + rr) * d + h * 64 + c] = o / s_st[rr];
       }
     }
   }
@@ -488,6 +490,7 @@ __device__ __forceinline__ CrossScratch cross_scratch(unsigned char* p) {
 // lane = output dims (lane, lane + 32); the chunk statistics sit one per lane and are broadcast by shuffles.
 // Every load is in flight before the first use (a loop with a run-time bound would pay one L2 round trip per
 // chunk); chunks are combined in chunk order => deterministic.
+template <bool SPLIT_OUT>
 __device__ __forceinline__ void cross_attn_fold(const DecModel* m, int T, int h, int nch) {
   const int d = m->d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (WM_DEC_THREADS >> 5);
@@ -512,13 +515,18 @@ __device__ __forceinline__ void cross_attn_fold(const DecModel* m, int T, int h,
         num1 = fmaf(w, v1[cc], num1);
         den = fmaf(w, l, den);
       }
-    float* o = m->attn + (size_t)rr * d + h * 64;
-    o[lane] = num0 / den;
-    o[32 + lane] = num1 / den;
+    if (SPLIT_OUT) {   // ring kernel: operand format of the cross-O projection (common.cuh: store_split)
+      store_split(m->attn + (size_t)rr * d, h * 64 + lane, num0 / den);
+      store_split(m->attn + (size_t)rr * d, h * 64 + 32 + lane, num1 / den);
+    } else {
+      float* o = m->attn + (size_t)rr * d + h * 64;
+      o[lane] = num0 / den;
+      o[32 + lane] = num1 / den;
+    }
   }
 }
 
-template <class AfterQK, class AfterPV>
+template <bool SPLIT_OUT, class AfterQK, class AfterPV>
 __device__ __forceinline__ void cross_attn_core(const DecModel* m, int T, int h, int c, int nch, int nk, int nk_pad,
                                                 const __half* sK, const __half* sV, const CrossScratch& cs,
                                                 AfterQK&& after_qk, AfterPV&& after_pv, unsigned long long* pr = nullptr) {
@@ -638,7 +646,7 @@ __device__ __forceinline__ void cross_attn_core(const DecModel* m, int T, int h,
   cta_sync();
   if (pr) pr[8] = wm_timer_ns();
   if (s_last) {
-    cross_attn_fold(m, T, h, nch);
+    cross_attn_fold<SPLIT_OUT>(m, T, h, nch);
   }
   if (pr) { pr[10] = wm_timer_ns(); pr[11] = s_last ? 1000ull : 0ull; }
 }
@@ -683,7 +691,7 @@ __device__ __forceinline__ void stage_cross_attn(const DecModel* m, int mode, in
       reinterpret_cast<uint4*>(sK)[nk * 9 + idx] = make_uint4(0, 0, 0, 0);
       reinterpret_cast<uint4*>(sV)[nk * 9 + idx] = make_uint4(0, 0, 0, 0);
     }
-    cross_attn_core(m, g.T, h, c, nch, nk, nk_pad, sK, sV, cs, [] {}, [] {});
+    cross_attn_core<false>(m, g.T, h, c, nch, nk, nk_pad, sK, sV, cs, [] {}, [] {});
   }
 }
 
@@ -1329,6 +1337,10 @@ void dec_build_stage_table(const DecModel& hm, int ncta, std::vector<CtaStage>& 
       c.n_begin = wk.n_begin; c.n_rows = wk.n_rows;
       c.N = g.N; c.ldo = g.ldo; c.out_row0 = g.out_row0;
       c.segs = wk.segs; c.seg = wk.seg; c.block = wk.block;
+      // activations that only ever feed one GEMM stage travel in the MMA operand format: the attention stages and
+      // the GELU epilogue of FC1 write it, O-proj / cross-O / FC2 skip their split pass
+      c.presplit = (stage == ST_OPROJ || stage == ST_CROSS_O || stage == ST_FC2) ? 1 : 0;
+      c.out_split = (stage == ST_FC1) ? 1 : 0;
     }
   }
 }
