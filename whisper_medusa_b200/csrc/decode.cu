@@ -753,7 +753,7 @@ __device__ __forceinline__ void stage_final_ln(const DecModel* m, int mode, int 
 #pragma unroll
     for (int i = 0; i < 10; ++i)
       if (i < nv) {
-        const float4 gg = g4[i * 32 + lane], bb = b4[i * 32 + lane];
+        const float4 gg = __ldg(g4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);   // (read-only path: may run ahead of the stores below)
         float4 y;
         y.x = (v[i].x - mean) * rstd * gg.x + bb.x;
         y.y = (v[i].y - mean) * rstd * gg.y + bb.y;
@@ -958,45 +958,59 @@ __device__ __noinline__ void stage_select_fin(const DecModel* m, int ncta) {
 // -----------------------------------------------------------------------------------------
 __device__ __noinline__ void stage_accept(const DecModel* m, int ncta) {
   __shared__ int s_a;
+  __shared__ int s_arg[WM_MAX_T];
+  __shared__ float s_thr[WM_MAX_T];
   DecState* st = m->st;
   const int K = m->K;
   const int nseg = select_nseg(m, ncta);
+  const int lane = threadIdx.x & 31;
   // fold the scan partials: argmax of every row, acceptance threshold of rows < K
   for (int r = threadIdx.x >> 5; r <= K; r += (WM_DEC_THREADS >> 5)) {   // warp per row
     const float temp = st->temperature;
     float M, Z, ent; int idx;
     select_fold(m, r, nseg, temp > 0.f ? 1.0f / temp : 1.0f, M, idx, Z, ent);
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
       st->row_argmax[r] = idx;
-      if (r < K && temp > 0.f)
-        st->row_thr[r] = fminf(st->post_thr, expf(ent) * st->post_alpha);   // ent = sum p log(p+1e-5) = -entropy
+      s_arg[r] = idx;
+      if (r < K && temp > 0.f) {
+        const float thr = fminf(st->post_thr, expf(ent) * st->post_alpha);   // ent = sum p log(p+1e-5) = -entropy
+        st->row_thr[r] = thr;
+        s_thr[r] = thr;
+      }
     }
   }
   cta_sync();
-  if (threadIdx.x == 0) {
+  // acceptance and loop state: warp 0, one chain position per lane (every cross-CTA value is fetched once, all
+  // loads in flight together; a serial walk would pay one L2 round trip per position)
+  if (threadIdx.x < 32) {
     const int L = st->L;
-    int a = 0;
-    if (st->temperature == 0.f) {
-      while (a < K && ldcg_i(&st->cand[a + 1]) == ldcg_i(&st->row_argmax[a])) ++a;
-    } else {
-      while (a < K && ldcg_f(&st->row_pc[a]) > ldcg_f(&st->row_thr[a])) ++a;
-    }
+    const float temp = st->temperature;
+    const int cand_l = (lane <= K) ? ldcg_i(&st->cand[lane]) : 0;
+    const float pc_l = (lane < K && temp != 0.f) ? ldcg_f(&st->row_pc[lane]) : 0.f;
+    const int cand_next = __shfl_down_sync(0xffffffffu, cand_l, 1);
+    bool ok = false;
+    if (lane < K) ok = (temp == 0.f) ? (cand_next == s_arg[lane]) : (pc_l > s_thr[lane]);
+    const unsigned int bal = __ballot_sync(0xffffffffu, ok);
+    const int a = __ffs(~bal) - 1;          // length of the accepted prefix (lanes >= K never vote ok => a <= K)
     int n_new = a + 1;
-    for (int i = 0; i <= a; ++i) st->ids[L + i] = ldcg_i(&st->cand[i]);
-    if (a == 0) { st->ids[L + 1] = ldcg_i(&st->row_argmax[0]); n_new = 2; }
-    bool eos = false;
-    for (int i = 0; i < n_new; ++i) eos |= (st->ids[L + i] == st->eos);
-    const int newL = L + n_new;
-    st->L = newL;
-    st->kv_len = (a == 0) ? newL - 1 : newL;
-    st->need_a = (a == 0) ? 1 : 0;
-    st->accept_last = a;
-    st->accept_hist[st->n_iter] = a;
-    st->n_iter += 1;
-    bool done = eos || newL >= st->max_length || newL + K >= st->max_length;
-    if (st->max_iters > 0 && st->n_iter >= st->max_iters) done = true;
-    if (done) st->done = 1;
-    s_a = a;
+    int id = cand_l;
+    if (a == 0) { n_new = 2; if (lane == 1) id = s_arg[0]; }
+    if (lane < n_new) st->ids[L + lane] = id;
+    const bool eos = __ballot_sync(0xffffffffu, lane < n_new && id == st->eos) != 0u;
+    if (lane == 0) {
+      const int newL = L + n_new;
+      st->L = newL;
+      st->kv_len = (a == 0) ? newL - 1 : newL;
+      st->need_a = (a == 0) ? 1 : 0;
+      st->accept_last = a;
+      const int it = st->n_iter;
+      st->accept_hist[it] = a;
+      st->n_iter = it + 1;
+      bool done = eos || newL >= st->max_length || newL + K >= st->max_length;
+      if (st->max_iters > 0 && it + 1 >= st->max_iters) done = true;
+      if (done) st->done = 1;
+      s_a = a;
+    }
   }
   cta_sync();
   const int a = s_a;

@@ -137,18 +137,6 @@ __host__ __device__ constexpr size_t cmax(size_t a, size_t b) { return a > b ? a
 __host__ __device__ constexpr size_t round128(size_t a) { return (a + 127) / 128 * 128; }
 __host__ __device__ constexpr int ring_nks(int d) { return (d % 256 == 0) ? 8 : (d % 128 == 0) ? 4 : (d % 64 == 0) ? 2 : 1; }
 
-// on-chip staging of the ring kernel's self-attention stage (stage_self_attn_ring)
-#define WM_SA_KEYS 480                       // keys staged on-chip (longer caches fall back to the generic stage)
-#define WM_SA_KSTRIDE 144                    // bytes per staged K row (64 fp16 + 16 B pad)
-#define WM_SA_KGROUPS (WM_DEC_THREADS / 8)   // key groups of the P V phase
-#define WM_SA_VREGS ((WM_SA_KEYS + WM_SA_KGROUPS - 1) / WM_SA_KGROUPS)
-__host__ __device__ constexpr size_t self_attn_ring_smem_bytes() {
-  return (size_t)WM_SA_KEYS * WM_SA_KSTRIDE + (size_t)WM_SA_MAXR * 64 * sizeof(float) +
-         (size_t)WM_SA_MAXR * WM_SA_KEYS * sizeof(float) + (size_t)2 * WM_SA_MAXR * sizeof(float);
-}
-static_assert((size_t)(WM_DEC_THREADS / 32) * WM_SA_MAXR * 64 * sizeof(float) <= (size_t)WM_SA_KEYS * WM_SA_KSTRIDE,
-              "the P V partials alias the staged K rows");
-
 #define WM_XS_PADB 16   // bytes of X-row padding: stride = 16 (mod 128) => conflict-free LDS.128 / STS.128
 
 template <int D>
@@ -165,7 +153,7 @@ struct RingGeom {
   static constexpr int NV = (D + 127) / 128;          // float4 per lane of a row-per-warp pass
   // shared-memory map
   static constexpr size_t SCRATCH_OFF = (size_t)WM_RING_G * SLOT_BYTES;
-  static constexpr size_t SCRATCH = round128(cmax(cmax((size_t)16 * XS, cross_scratch_bytes()), cmax(self_attn_smem_bytes(), self_attn_ring_smem_bytes())));
+  static constexpr size_t SCRATCH = round128(cmax(cmax((size_t)16 * XS, cross_scratch_bytes()), self_attn_smem_bytes()));
   static constexpr size_t PARTIAL_OFF = SCRATCH_OFF + SCRATCH;
   static constexpr size_t PARTIAL = round128(cmax((size_t)8 * 256 * sizeof(float), (size_t)2 * D * sizeof(float)));
   static constexpr size_t MODEL_OFF = PARTIAL_OFF + PARTIAL;
@@ -241,25 +229,16 @@ struct RingState {
   unsigned int xpar;   // parity of the activation-copy barrier
   unsigned int ppar;   // parity of the LayerNorm-vector barrier
 };
-// The state crosses the (out-of-line) stage functions packed in one register: slot | par << 2 | xpar << 3 | ppar << 4.
-__device__ __forceinline__ unsigned int ring_pack(const RingState& r) {
-  return (unsigned int)r.slot | (r.par << 2) | (r.xpar << 3) | (r.ppar << 4);
-}
-__device__ __forceinline__ RingState ring_unpack(unsigned int w) {
-  RingState r;
-  r.slot = (int)(w & 3u); r.par = (w >> 2) & 1u; r.xpar = (w >> 3) & 1u; r.ppar = (w >> 4) & 1u;
-  return r;
-}
 
 // ---------------------------------------------------------------------------------------------
 // GEMM stage fed from the ring (compute warps).  `sd` = this CTA's resolved record (shared memory).
 // ---------------------------------------------------------------------------------------------
 template <int D>
-__device__ __noinline__ unsigned int stage_gemm_ring(unsigned int rstate, unsigned char* smem, const DecModel* m, const CtaStage* sd,
-                                                    int Tpass, int base, unsigned long long* pr) {
+__device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* smem, const DecModel* m, const CtaStage* sd,
+                                                int Tpass, int base, unsigned long long* pr) {
   using G = RingGeom<D>;
-  RingState rs = ring_unpack(rstate);
   __shared__ int s_last;
+  __shared__ float2 s_stat[WM_MAX_T];
   const int n_rows = sd->n_rows;
   unsigned char* const xb = smem + G::SCRATCH_OFF;
   float* const partial = reinterpret_cast<float*>(smem + G::PARTIAL_OFF);
@@ -271,7 +250,7 @@ __device__ __noinline__ unsigned int stage_gemm_ring(unsigned int rstate, unsign
     // no rows for this CTA (narrow models; the chunk table has no entry either) -- but the LayerNorm vectors
     // were sent to every CTA: consume that phase
     if (sd->ln) { while (!mbar_try_wait(pbar, rs.ppar)) { } rs.ppar ^= 1u; }
-    return ring_pack(rs);
+    return;
   }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int nwarps = WM_DEC_THREADS >> 5;
@@ -283,84 +262,69 @@ __device__ __noinline__ unsigned int stage_gemm_ring(unsigned int rstate, unsign
     pr[7] = global_timer_ns();
     pr[11] = mbar_try_wait(full + rs.slot, rs.par) ? 1000ull : 0ull;   // weights already here?
   }
-  // ---- X rows.  Plain / presplit stages: global (L2) -> shared, one bulk copy per row.  LayerNorm stages: each
-  // warp pulls its row straight into registers with L2-coherent vector loads (all in flight at once): the raw row
-  // never visits shared memory.
-  if (warp == 0 && !ln) {
+  // ---- X rows: global (L2) -> shared, one bulk copy per row ----
+  if (warp == 0) {
     if (lane == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of the buffer vs async writes
       mbar_expect_tx(xbar, (uint32_t)(T * D * 4));
     }
     __syncwarp();
     if (lane < T) bulk_g2s(xb + (size_t)lane * G::XS, sd->X + (size_t)lane * sd->x_ld, (uint32_t)(D * 4), xbar);
-  } else if (warp == nwarps - 1) {
+  } else if (warp == 1) {
     // this CTA's bias slice of the NEXT GEMM stage -> L2 (biases are cold: 2 GB of weights pass through L2 per iteration)
     if (lane < sd->pf_bias_lines) prefetch_l2(reinterpret_cast<const unsigned char*>(sd->pf_bias) + (size_t)lane * 128);
   }
+  while (!mbar_try_wait(xbar, rs.xpar)) { }
+  rs.xpar ^= 1u;
+  if (pr) pr[8] = global_timer_ns();
   if (ln) {
-    float4 v[G::NV];
-#pragma unroll
-    for (int i = 0; i < G::NV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp < T) {
-      const float4* src = reinterpret_cast<const float4*>(sd->X + (size_t)warp * sd->x_ld) + lane;
-#pragma unroll
-      for (int i = 0; i < G::NV; ++i)
-        if (i * 32 + lane < G::NV4) v[i] = __ldcg(src + i * 32);
-    }
-    // gamma / beta were bulk-copied into the (idle) partial buffer during the preceding barrier
-    while (!mbar_try_wait(pbar, rs.ppar)) { }
-    rs.ppar ^= 1u;
-    if (pr) pr[8] = global_timer_ns();
-    // one warp per row, the row in registers: lane l holds float4 columns l, l+32, ...; statistics (two passes
-    // over the registers), normalisation and the hi/lo split without a CTA barrier in between
+    // statistics: one warp per row, lane l sums float4 columns l, l+32, ... (two passes over shared memory)
     for (int r = warp; r < T; r += nwarps) {
-      uint4* const row = reinterpret_cast<uint4*>(xb + (size_t)r * G::XS) + lane;
-      if (r != warp) {   // T > 11 rows: second round
-        const float4* src = reinterpret_cast<const float4*>(sd->X + (size_t)r * sd->x_ld) + lane;
-#pragma unroll
-        for (int i = 0; i < G::NV; ++i)
-          if (i * 32 + lane < G::NV4) v[i] = __ldcg(src + i * 32);
-      }
+      const float4* x4 = reinterpret_cast<const float4*>(xb + (size_t)r * G::XS) + lane;
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < G::NV; ++i)
-        if (i * 32 + lane < G::NV4) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        if (i * 32 + lane < G::NV4) { const float4 v = x4[i * 32]; s += (v.x + v.y) + (v.z + v.w); }
       const float mean = warp_sum(s) / (float)D;
       float q = 0.f;
 #pragma unroll
       for (int i = 0; i < G::NV; ++i)
         if (i * 32 + lane < G::NV4) {
-          const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+          const float4 v = x4[i * 32];
+          const float a = v.x - mean, b = v.y - mean, c = v.z - mean, e = v.w - mean;
           q += (a * a + b * b) + (c * c + e * e);
         }
       const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-5f);
-#pragma unroll
-      for (int i = 0; i < G::NV; ++i)
-        if (i * 32 + lane < G::NV4) {
-          const float4 gg = reinterpret_cast<const float4*>(partial)[i * 32 + lane];
-          const float4 bb = reinterpret_cast<const float4*>(partial)[G::NV4 + i * 32 + lane];
-          float4 y;
-          y.x = (v[i].x - mean) * rstd * gg.x + bb.x;
-          y.y = (v[i].y - mean) * rstd * gg.y + bb.y;
-          y.z = (v[i].z - mean) * rstd * gg.z + bb.z;
-          y.w = (v[i].w - mean) * rstd * gg.w + bb.w;
-          row[i * 32] = split_hilo4(y);
-        }
+      if (lane == 0) s_stat[r] = make_float2(mean, rstd);
     }
-  } else {
-    while (!mbar_try_wait(xbar, rs.xpar)) { }
-    rs.xpar ^= 1u;
-    if (pr) pr[8] = global_timer_ns();
-  }
-  if (!ln && !sd->presplit) {
+    // gamma / beta were bulk-copied into the (idle) partial buffer during the preceding barrier
+    while (!mbar_try_wait(pbar, rs.ppar)) { }
+    rs.ppar ^= 1u;
+    cta_sync();
+    if (pr) pr[9] = global_timer_ns();
+    if (tid < G::NV4) {
+      const float4 gg = reinterpret_cast<const float4*>(partial)[tid];
+      const float4 bb = reinterpret_cast<const float4*>(partial)[G::NV4 + tid];
+      for (int r = 0; r < T; ++r) {
+        uint4* p = reinterpret_cast<uint4*>(xb + (size_t)r * G::XS) + tid;
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        const float2 st = s_stat[r];
+        float4 y;
+        y.x = (v.x - st.x) * st.y * gg.x + bb.x;
+        y.y = (v.y - st.x) * st.y * gg.y + bb.y;
+        y.z = (v.z - st.x) * st.y * gg.z + bb.z;
+        y.w = (v.w - st.x) * st.y * gg.w + bb.w;
+        *p = split_hilo4(y);
+      }
+    }
+  } else if (!sd->presplit) {
     // flat over the buffer (the 16-byte row pad is converted along: no index arithmetic)
     uint4* p = reinterpret_cast<uint4*>(xb);
     const int n16 = T * (G::XS >> 4);
     for (int idx = tid; idx < n16; idx += WM_DEC_THREADS) p[idx] = split_hilo4(*reinterpret_cast<const float4*>(p + idx));
   }
-  // (presplit: the producing stage already wrote the rows in the hi/lo operand format)
   if (pr) pr[10] = global_timer_ns();
-  if (!sd->presplit) cta_sync();   // (presplit: every thread saw the copies complete, nothing was rewritten)
+  cta_sync();
   if (pr) pr[3] = global_timer_ns();
   const int units = (n_rows + 15) >> 4;
   const bool ksplit = sd->segs > 1;
@@ -371,25 +335,6 @@ __device__ __noinline__ unsigned int stage_gemm_ring(unsigned int rstate, unsign
   // named barrier 3 = "partials of unit u read" (the partial buffer is single: its rewrite waits for the readers).
   constexpr int NE = WM_DEC_THREADS - G::NKS * 32;   // epilogue threads
   if (warp < G::NKS) {
-    // X-stationary: this warp's k-slice of the activations (A fragments, hi and lo, all 16 token rows) is read from
-    // shared memory ONCE and stays in registers for every unit of the stage -- per unit only the weights are read
-    // (the X re-read was 2/3 of the shared-memory traffic of a unit).
-    constexpr int NIT = G::KS / 32;
-    const bool t1 = (gq + 8) < T;   // token rows 8..15 contribute nothing when T <= 8 + gq
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    uint4 xp0[NIT], xp1[NIT], xq0[NIT], xq1[NIT];
-    {
-      const unsigned char* x0 = xb + (size_t)gq * G::XS + (size_t)(warp * G::KS + 8 * tq) * 4;
-      const unsigned char* x1 = x0 + (size_t)8 * G::XS;
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        // {hi(k,k+1), lo(k,k+1), hi(k+2,k+3), lo(k+2,k+3)} for k = it*32 + 8 tq and k + 4
-        xp0[it] = *reinterpret_cast<const uint4*>(x0 + it * 128);
-        xp1[it] = *reinterpret_cast<const uint4*>(x0 + it * 128 + 16);
-        xq0[it] = t1 ? *reinterpret_cast<const uint4*>(x1 + it * 128) : z;
-        xq1[it] = t1 ? *reinterpret_cast<const uint4*>(x1 + it * 128 + 16) : z;
-      }
-    }
     for (int u = 0; u < units; ++u) {
       const int nvalid = min(16, n_rows - u * 16);
       if (pr && u == 0) { pr[12] = mbar_try_wait(full + rs.slot, rs.par) ? 1000ull : 0ull; pr[13] = global_timer_ns(); }
@@ -399,14 +344,22 @@ __device__ __noinline__ unsigned int stage_gemm_ring(unsigned int rstate, unsign
       const bool v0 = gq < nvalid, v1 = (gq + 8) < nvalid;
       const __half* w0p = sl + (size_t)gq * (G::ROW_STRIDE / 2) + warp * G::KS + 8 * tq;
       const __half* w1p = w0p + (size_t)8 * (G::ROW_STRIDE / 2);
+      const unsigned char* x0 = xb + (size_t)gq * G::XS + (size_t)(warp * G::KS + 8 * tq) * 4;
+      const unsigned char* x1 = x0 + (size_t)8 * G::XS;
+      const bool t1 = (gq + 8) < T;   // token rows 8..15 contribute nothing when T <= 8 + gq
       // four independent accumulator chains: (n8 tile 0 / 1) x (hi / lo part of X)
       float c0h[4] = {0.f, 0.f, 0.f, 0.f}, c0l[4] = {0.f, 0.f, 0.f, 0.f};
       float c1h[4] = {0.f, 0.f, 0.f, 0.f}, c1l[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        const uint4 wa = v0 ? *reinterpret_cast<const uint4*>(w0p + it * 32) : z;
-        const uint4 wb = v1 ? *reinterpret_cast<const uint4*>(w1p + it * 32) : z;
-        const uint4 p0 = xp0[it], p1 = xp1[it], q0 = xq0[it], q1 = xq1[it];
+      for (int kk = 0; kk < G::KS; kk += 32) {
+        const uint4 wa = v0 ? *reinterpret_cast<const uint4*>(w0p + kk) : z;
+        const uint4 wb = v1 ? *reinterpret_cast<const uint4*>(w1p + kk) : z;
+        // {hi(k,k+1), lo(k,k+1), hi(k+2,k+3), lo(k+2,k+3)} for k = kk + 8 tq and k + 4
+        const uint4 p0 = *reinterpret_cast<const uint4*>(x0 + kk * 4);
+        const uint4 p1 = *reinterpret_cast<const uint4*>(x0 + kk * 4 + 16);
+        const uint4 q0 = t1 ? *reinterpret_cast<const uint4*>(x1 + kk * 4) : z;
+        const uint4 q1 = t1 ? *reinterpret_cast<const uint4*>(x1 + kk * 4 + 16) : z;
         mma_16816(c0h, p0.x, q0.x, p0.z, q0.z, wa.x, wa.y);
         mma_16816(c0l, p0.y, q0.y, p0.w, q0.w, wa.x, wa.y);
         mma_16816(c1h, p0.x, q0.x, p0.z, q0.z, wb.x, wb.y);
@@ -535,157 +488,6 @@ __device__ __noinline__ unsigned int stage_gemm_ring(unsigned int rstate, unsign
       }
     }
   }
-  return ring_pack(rs);
-}
-
-// ---------------------------------------------------------------------------------------------
-// causal self-attention of the ring kernel (same items as stage_self_attn: (head, group of R query rows), one
-// wave).  The generic stage reads K and V rows from L2 inside its loops -- several dependent round trips.  Here
-// every byte the item needs is requested up front: the K rows of the head by bulk copies into shared memory
-// (144-byte row stride: conflict-free LDS.128 with one key per lane), the V rows straight into registers
-// (thread = (key group of 44, 8 output dims), <= 11 keys each), the queries into shared memory; one L2 round trip
-// later everything is on-chip.  Writes the attention output in the hi/lo operand format of the O-projection.
-// ---------------------------------------------------------------------------------------------
-template <int D>
-__device__ __noinline__ unsigned int stage_self_attn_ring(unsigned int xpar, unsigned char* smem, const DecModel* m, int layer, int T, int base,
-                                                          int cta, int ncta, unsigned long long* pr) {
-  using G = RingGeom<D>;
-  const int H = m->H;
-  int R = (H * T + ncta - 1) / ncta;
-  if (R > WM_SA_MAXR) R = WM_SA_MAXR;
-  if (R < 1) R = 1;
-  const int groups = (T + R - 1) / R;
-  if (base + T > WM_SA_KEYS) {   // cache longer than the on-chip staging area: generic stage (K / V from L2)
-    PassGeom pg; pg.T = T; pg.base = base;
-    stage_self_attn<true>(m, MODE_B, layer, cta, ncta, smem + G::SCRATCH_OFF, &pg, pr);
-    return xpar;
-  }
-  const DecLayer& L = m->layers[layer];
-  unsigned char* const sK = smem + G::SCRATCH_OFF;                                   // [WM_SA_KEYS][144 B]
-  float* const s_acc = reinterpret_cast<float*>(sK);                                 // [warps][R][64], after the scores
-  float* const s_q = reinterpret_cast<float*>(sK + (size_t)WM_SA_KEYS * WM_SA_KSTRIDE);   // [R][64]
-  float* const s_p = s_q + WM_SA_MAXR * 64;                                          // [R][WM_SA_KEYS]
-  float* const s_st = s_p + WM_SA_MAXR * WM_SA_KEYS;                                 // [R] sum
-  uint64_t* const xbar = reinterpret_cast<uint64_t*>(smem + G::BAR_OFF) + 2 * WM_RING_G;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int nwarps = WM_DEC_THREADS >> 5;
-  for (int item = cta; item < H * groups; item += ncta) {
-    const int h = item / groups, t0 = (item - h * groups) * R;
-    const int rg = min(R, T - t0);                 // rows in this group
-    const int nk_max = base + t0 + rg;             // keys of the last row of the group
-    if (item != cta) cta_sync();                   // the previous item is done with the buffers
-    // ---- everything in flight at once ----
-    if (warp == 0) {
-      if (lane == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(xbar, (uint32_t)(nk_max * 128));
-      }
-      __syncwarp();
-      const __half* kh = L.self_k + h * 64;
-      for (int j = lane; j < nk_max; j += 32) bulk_g2s(sK + (size_t)j * WM_SA_KSTRIDE, kh + (size_t)j * D, 128u, xbar);
-    } else if (tid - 32 < rg * 16) {
-      const int r = (tid - 32) >> 4, c4 = (tid - 32) & 15;
-      reinterpret_cast<float4*>(s_q)[r * 16 + c4] = ldcg_f4(m->q + (size_t)(t0 + r) * D + h * 64 + c4 * 4);
-    }
-    const int kg = tid >> 3, dg = tid & 7;
-    uint4 vv[WM_SA_VREGS];
-    {
-      const __half* vh = L.self_v + h * 64 + dg * 8;
-#pragma unroll
-      for (int i = 0; i < WM_SA_VREGS; ++i) {
-        const int jj = kg + i * WM_SA_KGROUPS;
-        vv[i] = (jj < nk_max) ? ldcg_u4(vh + (size_t)jj * D) : make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-    while (!mbar_try_wait(xbar, xpar)) { }
-    xpar ^= 1u;
-    cta_sync();   // queries visible
-    if (pr) pr[3] = global_timer_ns();
-    // ---- scores (scaled by head_dim^-0.5; HF scales q, a power of two, so this is identical): one key per thread,
-    // its row in registers, all rows of the group ----
-    for (int j = tid; j < nk_max; j += WM_DEC_THREADS) {
-      uint4 kr[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) kr[c] = *reinterpret_cast<const uint4*>(sK + (size_t)j * WM_SA_KSTRIDE + c * 16);
-#pragma unroll
-      for (int r = 0; r < WM_SA_MAXR; ++r)
-        if (r < rg) {
-          const float4* q4 = reinterpret_cast<const float4*>(s_q + r * 64);
-          float s = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const __half2* k2 = reinterpret_cast<const __half2*>(&kr[c]);
-            const float4 qa = q4[2 * c], qb = q4[2 * c + 1];
-            const float2 f0 = __half22float2(k2[0]), f1 = __half22float2(k2[1]);
-            const float2 f2 = __half22float2(k2[2]), f3 = __half22float2(k2[3]);
-            s = fmaf(qa.x, f0.x, s); s = fmaf(qa.y, f0.y, s); s = fmaf(qa.z, f1.x, s); s = fmaf(qa.w, f1.y, s);
-            s = fmaf(qb.x, f2.x, s); s = fmaf(qb.y, f2.y, s); s = fmaf(qb.z, f3.x, s); s = fmaf(qb.w, f3.y, s);
-          }
-          s_p[r * WM_SA_KEYS + j] = (j <= base + t0 + r) ? s * 0.125f : -INFINITY;   // causal
-        }
-    }
-    cta_sync();
-    if (pr) pr[4] = global_timer_ns();
-    // ---- softmax statistics: one warp per row ----
-    if (warp < rg) {
-      const int nk = base + t0 + warp + 1;
-      float* p = s_p + warp * WM_SA_KEYS;
-      float mx = -INFINITY;
-      for (int jj = lane; jj < nk; jj += 32) mx = fmaxf(mx, p[jj]);
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int jj = lane; jj < nk; jj += 32) { const float e = expf(p[jj] - mx); p[jj] = e; sum += e; }
-      sum = warp_sum(sum);
-      if (lane == 0) s_st[warp] = sum;
-    }
-    cta_sync();
-    if (pr) pr[5] = global_timer_ns();
-    // ---- P V out of the registers; the 4 key groups of a warp are folded by shuffles, the warps through shared
-    // memory (the K rows are dead by now) ----
-#pragma unroll
-    for (int r = 0; r < WM_SA_MAXR; ++r)
-      if (r < rg) {
-        const int nk = base + t0 + r + 1;
-        const float* p = s_p + r * WM_SA_KEYS;
-        float a[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) a[e] = 0.f;
-#pragma unroll
-        for (int i = 0; i < WM_SA_VREGS; ++i) {
-          const int jj = kg + i * WM_SA_KGROUPS;
-          if (jj < nk) {
-            const float pj = p[jj];
-            const __half2* v2 = reinterpret_cast<const __half2*>(&vv[i]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(v2[e]);
-              a[2 * e] = fmaf(pj, f.x, a[2 * e]);
-              a[2 * e + 1] = fmaf(pj, f.y, a[2 * e + 1]);
-            }
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          a[e] += __shfl_xor_sync(0xffffffffu, a[e], 8);
-          a[e] += __shfl_xor_sync(0xffffffffu, a[e], 16);
-        }
-        if (lane < 8) {
-          float4* o = reinterpret_cast<float4*>(s_acc + ((size_t)warp * WM_SA_MAXR + r) * 64 + lane * 8);
-          o[0] = make_float4(a[0], a[1], a[2], a[3]);
-          o[1] = make_float4(a[4], a[5], a[6], a[7]);
-        }
-      }
-    cta_sync();
-    if (pr) pr[6] = global_timer_ns();
-    if (tid < rg * 64) {
-      const int rr = tid >> 6, c = tid & 63;
-      float o = 0.f;
-#pragma unroll
-      for (int w = 0; w < nwarps; ++w) o += s_acc[((size_t)w * WM_SA_MAXR + rr) * 64 + c];
-      store_split(m->attn + (size_t)(t0 + rr) * D, h * 64 + c, o / s_st[rr]);
-    }
-  }
-  return xpar;   // parity of the activation-copy barrier (RingState::xpar)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -801,11 +603,11 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
     else if (mode == MODE_B) { pgv.T = m->K + 1; pgv.base = L0; }
     else { pgv.T = 1; pgv.base = L0 - 1; }
     if (is_gemm_stage(stage)) {
-      rs = ring_unpack(stage_gemm_ring<D>(ring_pack(rs), smem, m, sd, pgv.T, pgv.base, pr));
+      stage_gemm_ring<D>(rs, smem, m, sd, pgv.T, pgv.base, pr);
     } else if (stage == ST_CROSS_ATTN) {
       stage_cross_attn_ring<D>(rs, smem, m, pgv.T, cta, ncta, pr);
     } else if (stage == ST_SELF_ATTN) {
-      rs.xpar = stage_self_attn_ring<D>(rs.xpar, smem, m, sd->layer, pgv.T, pgv.base, cta, ncta, pr);
+      stage_self_attn<true>(m, mode, sd->layer, cta, ncta, smem + G::SCRATCH_OFF, &pgv, pr);
     } else {
       run_stage<false>(m, stage, mode, sd->layer, cta, ncta, smem + G::SCRATCH_OFF, &pgv, pr);
     }
