@@ -41,12 +41,12 @@ METRIC = "effective decoded tokens/sec (post-verify) Whisper-large-v2+Medusa"
 
 def ncu_traffic_bytes(args):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r1_ring_kernel_ncu.json) -- only meaningful for the configuration that
+    `ncu --set full` capture (profiles/r1b_ring_kernel_ncu.json) -- only meaningful for the configuration that
     capture was taken on (large-v2, 10 linear heads, persistent mode); null otherwise."""
     if not (args.preset == "large-v2" and args.heads == 10 and args.heads_type == "base_head" and args.mode == "persistent"):
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ring_kernel_ncu.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1b_ring_kernel_ncu.json")) as f:
             pl = json.load(f)["per_launch"]
         return int(pl["dram_bytes_read"]) + int(pl["dram_bytes_write"])
     except Exception:
