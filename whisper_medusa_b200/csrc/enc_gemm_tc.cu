@@ -25,10 +25,10 @@ namespace wm {
 #define TC_BM 128
 #define TC_BN 128
 #define TC_BK 64
-#define TC_STAGES 6
+#define TC_STAGES 3
 #define TC_THREADS 192
 #define TC_TMEM_COLS 128
-#define TC_STAGE_BYTES ((TC_BM + TC_BN) * TC_BK * 2)
+#define TC_STAGE_BYTES ((TC_BM + TC_BN) * TC_BK * 2)   /* layout of a stage for every tile width: A at 0, W at 16 KB */
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count) {
@@ -70,8 +70,8 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
 }
 // kind::f16 instruction descriptor (cute UMMA::InstrDescriptor): c_format F32 (bit 4), a/b F16 (0),
 // both K-major (bits 15,16 = 0), n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29)
-__device__ __forceinline__ constexpr uint32_t tc_instr_desc() {
-  return (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+__device__ __forceinline__ constexpr uint32_t tc_instr_desc(int bn) {
+  return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 __device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -109,15 +109,15 @@ struct TcArgs {
   const float* pos;
 };
 
-template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int EPI, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 2)
 enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // stage s: A tile [128 rows][64 halfs] at s*32K, W tile at s*32K + 16K (both 1024-B aligned, SW128)
   __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tmem_full;
   __shared__ uint32_t s_tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int KT = a.K / TC_BK;
   const uint32_t smem_base = tc_smem_u32(smem_raw);
 
@@ -150,7 +150,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t ph = (kt / TC_STAGES) & 1;
         tc_mbar_wait(tc_smem_u32(&s_empty[s]), ph ^ 1);
         const uint32_t full = tc_smem_u32(&s_full[s]);
-        tc_mbar_expect_tx(full, TC_STAGE_BYTES);
+        tc_mbar_expect_tx(full, (TC_BM + BN) * TC_BK * 2);
         tc_tma_load_2d(smem_base + s * TC_STAGE_BYTES, &map_a, kt * TC_BK, m0, full);
         tc_tma_load_2d(smem_base + s * TC_STAGE_BYTES + TC_BM * TC_BK * 2, &map_w, kt * TC_BK, n0, full);
       }
@@ -158,7 +158,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = tc_instr_desc();
+      const uint32_t idesc = tc_instr_desc(BN);
       for (int kt = 0; kt < KT; ++kt) {
         const int s = kt % TC_STAGES;
         const uint32_t ph = (kt / TC_STAGES) & 1;
@@ -183,7 +183,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < a.M;
 #pragma unroll 1
-    for (int cb = 0; cb < TC_BN / 32; ++cb) {
+    for (int cb = 0; cb < BN / 32; ++cb) {
       uint32_t v[32];
       tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
       if (!row_ok) continue;
@@ -250,12 +250,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp16 view [rows][K] with row stride `ld` elements, boxes of [128 rows][64 columns], SWIZZLE_128B
-static bool make_map(CUtensorMap* map, const __half* base, uint64_t rows, uint64_t K, uint64_t ld) {
+static bool make_map(CUtensorMap* map, const __half* base, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {K, rows};
   cuuint64_t strides[1] = {ld * sizeof(__half)};
-  cuuint32_t box[2] = {TC_BK, TC_BM};
+  cuuint32_t box[2] = {TC_BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -268,7 +268,9 @@ static const size_t kTcSmem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
 cudaError_t enc_gemm_tc_configure() {
   cudaError_t e;
 #define WM_SET(EPI)                                                                                              \
-  e = cudaFuncSetAttribute(enc_gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem); \
+  e = cudaFuncSetAttribute(enc_gemm_tc_kernel<EPI, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem); \
+  if (e != cudaSuccess) return e;                                                                                 \
+  e = cudaFuncSetAttribute(enc_gemm_tc_kernel<EPI, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);  \
   if (e != cudaSuccess) return e;
   WM_SET(ENC_EPI_BIAS_F16)
   WM_SET(ENC_EPI_BIAS_GELU_F16)
@@ -281,31 +283,44 @@ cudaError_t enc_gemm_tc_configure() {
 // `a_rows` = rows of the A view that may be touched (the allocation is padded accordingly)
 cudaError_t enc_gemm_tc(const EncGemmArgs& g, int a_rows, cudaStream_t s, int64_t* n_launch) {
   if (g.N % TC_BN != 0 || g.K % TC_BK != 0 || (g.lda % 8) != 0) return cudaErrorInvalidValue;
-  typedef std::tuple<const void*, uint64_t, uint64_t, uint64_t> Key;
+  typedef std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t> Key;
   static thread_local std::map<Key, CUtensorMap> cache;
-  auto get = [&](const __half* base, uint64_t rows, uint64_t K, uint64_t ld, CUtensorMap* out) -> bool {
-    Key k(base, rows, K, ld);
+  auto get = [&](const __half* base, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows, CUtensorMap* out) -> bool {
+    Key k(base, rows, K, ld, box_rows);
     auto it = cache.find(k);
     if (it == cache.end()) {
       CUtensorMap m;
-      if (!make_map(&m, base, rows, K, ld)) return false;
+      if (!make_map(&m, base, rows, K, ld, box_rows)) return false;
       it = cache.emplace(k, m).first;
     }
     *out = it->second;
     return true;
   };
   CUtensorMap ma, mw;
-  if (!get(g.A, (uint64_t)a_rows, (uint64_t)g.K, (uint64_t)g.lda, &ma)) return cudaErrorInvalidValue;
-  if (!get(g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.K, &mw)) return cudaErrorInvalidValue;
+  const int bn = (g.N <= 1536 && g.N % 64 == 0) ? 64 : TC_BN;   // narrow outputs: twice the tiles, all SMs busy
+  if (!get(g.A, (uint64_t)a_rows, (uint64_t)g.K, (uint64_t)g.lda, TC_BM, &ma)) return cudaErrorInvalidValue;
+  if (!get(g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.K, (uint32_t)bn, &mw)) return cudaErrorInvalidValue;
   TcArgs a;
   a.M = g.M; a.N = g.N; a.K = g.K; a.epi = g.epi; a.bias = g.bias; a.out16 = g.out16; a.ldo16 = g.ldo16;
   a.out32 = g.out32; a.ldo32 = g.ldo32; a.pos = g.pos;
-  dim3 grid(g.N / TC_BN, (g.M + TC_BM - 1) / TC_BM);
+  dim3 grid(g.N / bn, (g.M + TC_BM - 1) / TC_BM);
   switch (g.epi) {
-    case ENC_EPI_BIAS_F16: enc_gemm_tc_kernel<ENC_EPI_BIAS_F16><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a); break;
-    case ENC_EPI_BIAS_GELU_F16: enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_F16><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a); break;
-    case ENC_EPI_BIAS_RES_F32: enc_gemm_tc_kernel<ENC_EPI_BIAS_RES_F32><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a); break;
-    case ENC_EPI_BIAS_GELU_POS_F32: enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_POS_F32><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a); break;
+    case ENC_EPI_BIAS_F16:
+      if (bn == 64) enc_gemm_tc_kernel<ENC_EPI_BIAS_F16, 64><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
+      else enc_gemm_tc_kernel<ENC_EPI_BIAS_F16, 128><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
+      break;
+    case ENC_EPI_BIAS_GELU_F16:
+      if (bn == 64) enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_F16, 64><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
+      else enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_F16, 128><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
+      break;
+    case ENC_EPI_BIAS_RES_F32:
+      if (bn == 64) enc_gemm_tc_kernel<ENC_EPI_BIAS_RES_F32, 64><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
+      else enc_gemm_tc_kernel<ENC_EPI_BIAS_RES_F32, 128><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
+      break;
+    case ENC_EPI_BIAS_GELU_POS_F32:
+      if (bn == 64) enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_POS_F32, 64><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
+      else enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_POS_F32, 128><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
+      break;
     default: return cudaErrorInvalidValue;
   }
   if (n_launch) ++*n_launch;
