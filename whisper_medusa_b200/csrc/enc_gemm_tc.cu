@@ -7,7 +7,8 @@
 //   warp 1  : MMA issuer     -- one elected thread issues tcgen05.mma.cta_group::1.kind::f16
 //                               (M=128, N=128, K=16) x4 per stage, accumulator = 128 TMEM columns;
 //                               tcgen05.commit releases the stage (`empty`) / signals the epilogue
-//   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns per instruction) -> registers ->
+//   warps 2-9: epilogue      -- two warps per TMEM lane quarter (alternating 32-column blocks): tcgen05.ld
+//                               (32 lanes x 32 columns per instruction) -> registers ->
 //                               bias / GELU / residual / position epilogue -> global
 // The A operand may be an "implicit im2col" view: conv1/conv2 read a time-major activation whose
 // GEMM rows overlap (row stride 80 resp. 2d elements) -- the TMA tensor map simply carries that
@@ -26,7 +27,7 @@ namespace wm {
 #define TC_BN 128
 #define TC_BK 64
 #define TC_STAGES 3
-#define TC_THREADS 192
+#define TC_THREADS 320
 #define TC_TMEM_COLS 128
 #define TC_STAGE_BYTES ((TC_BM + TC_BN) * TC_BK * 2)   /* layout of a stage for every tile width: A at 0, W at 16 KB */
 
@@ -183,7 +184,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < a.M;
 #pragma unroll 1
-    for (int cb = 0; cb < BN / 32; ++cb) {
+    for (int cb = (warp - 2) >> 2; cb < BN / 32; cb += 2) {
       uint32_t v[32];
       tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
       if (!row_ok) continue;
