@@ -1,9 +1,10 @@
 // Encoder-side dense GEMM on the 5th-generation tensor cores (sm_100a):
 //   C[M,N] = A[M,K] * W[N,K]^T   fp16 operands (both K-major), fp32 accumulation in TMEM.
 //
-// Structure (one 128x128 output tile per CTA, K swept in 64-column blocks):
+// Structure (one 128x128 -- or 128x64 for narrow outputs -- tile per CTA, K swept in 64-column blocks; two CTAs per
+// SM, so one tile's epilogue overlaps the other's main loop):
 //   warp 0  : TMA producer   -- cp.async.bulk.tensor.2d (SWIZZLE_128B) of the A and W tiles into a
-//                               6-stage shared-memory ring, completion on `full` mbarriers
+//                               3-stage shared-memory ring, completion on `full` mbarriers
 //   warp 1  : MMA issuer     -- one elected thread issues tcgen05.mma.cta_group::1.kind::f16
 //                               (M=128, N=128, K=16) x4 per stage, accumulator = 128 TMEM columns;
 //                               tcgen05.commit releases the stage (`empty`) / signals the epilogue
