@@ -138,6 +138,55 @@ def test_checkpoint_directory_roundtrip(tmp_path):
     assert m.get_medusa_choice() == [1] * 5
 
 
+def test_checkpoint_directory_variants(tmp_path):
+    """The layouts HF's save_pretrained produces for the reference's checkpoints: sharded
+    safetensors with an index, the legacy pytorch_model.bin, fp32 tensors.  The packed engine tensors must be
+    the same whichever container the weights came in."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from whisper_medusa_b200.weights import engine_tensors
+
+    cfg = preset_config("micro", heads=4)
+    sd = synthetic_state_dict(cfg, seed=5)
+    ref = {k: v.clone() for k, v in engine_tensors(cfg, sd)}
+    tied = "whisper_model.proj_out.weight"
+
+    def check(path):
+        m = WhisperMedusaModel.from_pretrained(str(path))
+        got = dict(engine_tensors(m.config, m._state_dict))
+        assert set(got) == set(ref)
+        for k in ref:
+            assert got[k].dtype == ref[k].dtype and torch.equal(got[k], ref[k]), k
+
+    # (1) two safetensors shards + index, tensors stored in fp32 (the reference's default dtype)
+    d1 = tmp_path / "sharded"
+    d1.mkdir()
+    cfg.save_pretrained(str(d1))
+    keys = sorted(k for k in sd if k != tied)
+    half = len(keys) // 2
+    wm = {}
+    for i, part in enumerate((keys[:half], keys[half:])):
+        fn = f"model-{i + 1:05d}-of-00002.safetensors"
+        save_file({k: sd[k].to(torch.float32).contiguous() for k in part}, str(d1 / fn))
+        wm.update({k: fn for k in part})
+    (d1 / "model.safetensors.index.json").write_text(json.dumps({"metadata": {}, "weight_map": wm}))
+    check(d1)
+    # (2) legacy pytorch_model.bin
+    d2 = tmp_path / "bin"
+    d2.mkdir()
+    cfg.save_pretrained(str(d2))
+    torch.save({k: v for k, v in sd.items() if k != tied}, str(d2 / "pytorch_model.bin"))
+    check(d2)
+    # (3) nothing to load
+    d3 = tmp_path / "empty"
+    d3.mkdir()
+    cfg.save_pretrained(str(d3))
+    with pytest.raises(OSError):
+        WhisperMedusaModel.from_pretrained(str(d3))
+
+
 def test_generate_argument_errors_match_reference():
     cfg = preset_config("micro", heads=4)
     m = WhisperMedusaModel(cfg, None)

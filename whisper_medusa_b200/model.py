@@ -39,6 +39,33 @@ def _check(lib, handle, rc: int, what: str) -> None:
         raise EngineError(f"{what}: {lib.wm_strerror(rc).decode()} ({rc}) {msg}")
 
 
+def _load_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    """Weights of an HF checkpoint directory, whichever way `save_pretrained` wrote them: one
+    ``model.safetensors``, shards listed in ``model.safetensors.index.json`` (what HF writes above its
+    shard size -- whisper-large-v2 in fp32 is 6.2 GB), or the legacy ``pytorch_model.bin`` (+ index).
+    Any floating dtype is accepted: the packer casts matrices to fp16 and vectors to fp32 (weights.py)."""
+    import json
+
+    def shards(index_file: str) -> List[str]:
+        with open(os.path.join(path, index_file)) as f:
+            return sorted(set(json.load(f)["weight_map"].values()))
+
+    sd: Dict[str, torch.Tensor] = {}
+    if os.path.isfile(os.path.join(path, "model.safetensors")) or os.path.isfile(os.path.join(path, "model.safetensors.index.json")):
+        from safetensors.torch import load_file
+
+        files = ["model.safetensors"] if os.path.isfile(os.path.join(path, "model.safetensors")) else shards("model.safetensors.index.json")
+        for fn in files:
+            sd.update(load_file(os.path.join(path, fn)))
+    elif os.path.isfile(os.path.join(path, "pytorch_model.bin")) or os.path.isfile(os.path.join(path, "pytorch_model.bin.index.json")):
+        files = ["pytorch_model.bin"] if os.path.isfile(os.path.join(path, "pytorch_model.bin")) else shards("pytorch_model.bin.index.json")
+        for fn in files:
+            sd.update(torch.load(os.path.join(path, fn), map_location="cpu", weights_only=True))
+    else:
+        raise OSError(f"no model.safetensors / pytorch_model.bin (or their shard indices) in {path}")
+    return sd
+
+
 class GenerateTrace:
     """Per-call measurements (the reference collects ``accept_length_list`` but drops it,
     ``model.py:633,705``)."""
@@ -81,12 +108,7 @@ class WhisperMedusaModel:
         if not os.path.isdir(path):
             raise OSError(f"{path} is not a local directory (hub access is not available)")
         config = MedusaConfig.from_pretrained(path)
-        from safetensors.torch import load_file
-
-        st_file = os.path.join(path, "model.safetensors")
-        if not os.path.isfile(st_file):
-            raise OSError(f"{st_file} not found")
-        sd = load_file(st_file)
+        sd = _load_state_dict(path)
         if "whisper_model.proj_out.weight" not in sd:  # tied weight is not serialised by safetensors
             sd["whisper_model.proj_out.weight"] = sd["whisper_model.model.decoder.embed_tokens.weight"]
         model = cls(config, sd)
