@@ -118,8 +118,7 @@ def test_config_roundtrip_and_reference_errors(tmp_path):
     with pytest.raises(OSError):
         WhisperMedusaModel.from_pretrained(str(tmp_path / "missing"))
     with pytest.raises(NotImplementedError):
-        WhisperMedusaModel(preset_config("micro", heads=2, medusa_choices=[1, 2, 2]) if False else
-                           MedusaConfig(medusa_num_heads=2, medusa_hidden_size=128, medusa_choices=[1, 2, 2],
+        WhisperMedusaModel(MedusaConfig(medusa_num_heads=2, medusa_hidden_size=128, medusa_choices=[1, 2, 2],
                                         whisper_model_name="synthetic/whisper-micro"), None)
 
 
