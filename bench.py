@@ -6,10 +6,21 @@ Medusa-Linear heads, batch 1, 30 s synthetic audio  (BASELINE.json metric; confi
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference            # the CPU oracle (port of the reference) on host cores
 
-One "step" = one 30 s clip through the whole path (PCM -> log-mel -> encoder -> cross-K/V ->
-Medusa speculative loop to max_length).  Streams are independent (reference asserts batch 1,
-model.py:1451), so N GPUs run N streams per step with no data-path collective ("weak" scaling);
-the only collective is the NCCL broadcast of the packed weights at start-up.
+One "step" = one 30 s clip through the whole path (PCM -> log-mel -> encoder -> cross-K/V -> Medusa speculative
+loop until EOS / max_length), called the way the reference's evaluation script calls generate()
+(eval_whisper_medusa.py:61-65: language + exponential_decay_length_penalty=(140, 1.01)).  Streams are independent
+(reference asserts batch 1, model.py:1451), so N GPUs run N streams per step with no data-path collective ("weak"
+scaling); the only collective is the NCCL broadcast of the packed weights at start-up.
+
+Acceptance regimes.  Seeded random weights have no real acceptance statistics: under the default typical-acceptance
+constants the synthetic large-v2 model accepts all K candidates every iteration.  `posterior_alpha` (a field of the
+reference's MedusaGenerationConfig, medusa_utils.py:14-18) is the knob:
+    realistic (DEFAULT, headline)  alpha = 100   accept lengths 1 and 4 mixed, mean ~3   (3-5 tokens / iteration)
+    mixed0                          alpha = 230   accept-0 iterations (two sweeps) interleaved, mean ~1.5
+    best                            alpha = 0.3   every candidate accepted: K+1 tokens / iteration (upper bound)
+    zero                            alpha = 1e6   nothing accepted: 2 tokens / iteration, two sweeps (lower bound)
+The headline `value` / `e2e` / `roofline` are the realistic regime; `regimes` carries one short run of each of the
+others and `k_sweep` BASELINE configs[4] (K in {2, 4, 6, 10} at the realistic regime).
 
 Printed keys (one JSON line, rank 0):
   value       tokens/s of the decode loop with the encoder output resident in HBM (device time,
@@ -18,6 +29,8 @@ Printed keys (one JSON line, rank 0):
               PCM in, token ids out, H2D/D2H inside the timed region, wall clock max over ranks
   roofline    decode iteration vs the HBM roofline: algorithmic bytes of SURVEY.md 8(d)
   cpu_baseline the CPU oracle timed on this box's host cores on a bounded sample
+The run checks the tokens of stream 0 against the committed golden fixture of the same workload
+(tests/golden/large_linear_k10_mixed.npz) and fails loudly on a mismatch.
 """
 from __future__ import annotations
 
@@ -37,20 +50,24 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "effective decoded tokens/sec (post-verify) Whisper-large-v2+Medusa"
+REGIMES = {"realistic": 100.0, "mixed0": 230.0, "best": 0.3, "zero": 1.0e6}
+PENALTY = (140, 1.01)          # eval_whisper_medusa.py:61-65 defaults (--regulation-start / --regulation-factor)
+NCU_CAPTURE = os.path.join(ROOT, "profiles", "r2_ring_kernel_ncu.json")
 
 
 def ncu_traffic_bytes(args):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r1b_ring_kernel_ncu.json) -- only meaningful for the configuration that
-    capture was taken on (large-v2, 10 linear heads, persistent mode); null otherwise."""
+    `ncu --set full` capture of this workload (large-v2, 10 linear heads, persistent mode); null otherwise."""
     if not (args.preset == "large-v2" and args.heads == 10 and args.heads_type == "base_head" and args.mode == "persistent"):
         return None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1b_ring_kernel_ncu.json")) as f:
-            pl = json.load(f)["per_launch"]
-        return int(pl["dram_bytes_read"]) + int(pl["dram_bytes_write"])
-    except Exception:
-        return None
+    for path in (NCU_CAPTURE, os.path.join(ROOT, "profiles", "r1b_ring_kernel_ncu.json")):
+        try:
+            with open(path) as f:
+                pl = json.load(f)["per_launch"]
+            return int(pl["dram_bytes_read"]) + int(pl["dram_bytes_write"])
+        except Exception:  # noqa: BLE001
+            continue
+    return None
 
 
 def algorithmic_bytes(cfg, iterations: int, sweeps_a: int, n_mean: float):
@@ -125,49 +142,82 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def pick_threads(cfg) -> int:
-    """PyTorch eager on every hardware thread of a large host is far slower than on a subset (the
-    batch-1 decode is DRAM-bound and the thread barrier cost grows); time one vocabulary projection
-    for a few thread counts and keep the fastest.  `cores` in the JSON is what was actually used."""
-    n = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, n) if c <= n})
-    w = torch.randn(cfg.vocab_size, cfg.d_model)
-    x = torch.randn(1, cfg.d_model)
-    best, best_t = cands[0], float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        for _ in range(2):
-            torch.nn.functional.linear(x, w)
+def cpu_threads() -> int:
+    """Threads of the CPU arm: fixed rule (every hardware thread up to 32 -- PyTorch eager on more threads of a large
+    host is slower for this DRAM-bound batch-1 loop), so the number is reproducible from box to box."""
+    return max(1, min(32, os.cpu_count() or 1))
+
+
+class CpuReference:
+    """The CPU oracle (PyTorch eager fp32 restatement of the reference loop: one proj_out per head, two passes per
+    iteration, KV concatenation) on the same workload.  The encoder output of the clip is computed once (timed,
+    reported); a step is the first `max_iters` speculative iterations of the decode loop from that state."""
+
+    def __init__(self, cfg, sd, pcm, threads: int, alpha: float):
+        from oracle import medusa_ref as M
+        from oracle import whisper_ref as W
+
+        torch.set_num_threads(threads)
+        self.M, self.W, self.cfg = M, W, cfg
+        self.w = W.RefWeights(sd)
         t0 = time.perf_counter()
-        for _ in range(5):
-            torch.nn.functional.linear(x, w)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-    return best
-
-
-def cpu_reference_sample(cfg, sd, pcm, max_iters: int, threads: int):
-    """Time the CPU oracle (PyTorch eager fp32 restatement of the reference loop: one proj_out per
-    head, two passes per iteration, KV concatenation) on a bounded sample of the workload."""
-    from oracle import medusa_ref as M
-    from oracle import whisper_ref as W
-
-    torch.set_num_threads(threads)
-    w = W.RefWeights(sd)
-    t0 = time.perf_counter()
-    mel = torch.from_numpy(W.log_mel_spectrogram(pcm))
-    t1 = time.perf_counter()
-    with torch.inference_mode():
-        enc = W.encoder_forward(w, cfg, mel, "fp32")
+        mel = torch.from_numpy(W.log_mel_spectrogram(pcm))
+        t1 = time.perf_counter()
+        with torch.inference_mode():
+            self.enc = W.encoder_forward(self.w, cfg, mel, "fp32")
         t2 = time.perf_counter()
-        prompt = M.init_tokens(cfg, "en" if cfg.is_multilingual else None)
-        gp = M.gen_params(cfg, prompt)
-        tr = M.medusa_greedy_search(w, cfg, enc, prompt, gp, "fp32", max_iters=max_iters)
-    t3 = time.perf_counter()
-    n_tok = len(tr.sequences) - len(prompt)
-    return {"tokens": n_tok, "iters": tr.iters, "s_mel": t1 - t0, "s_encoder": t2 - t1, "s_decode": t3 - t2,
-            "tok_s_decode": n_tok / (t3 - t2), "tok_s_e2e": n_tok / (t3 - t0)}
+        self.s_mel, self.s_encoder = t1 - t0, t2 - t1
+        self.prompt = M.init_tokens(cfg, "en" if cfg.is_multilingual else None)
+        self.gp = M.gen_params(cfg, self.prompt, PENALTY, 448, posterior_alpha=alpha)
+
+    def step(self, max_iters: int):
+        t0 = time.perf_counter()
+        with torch.inference_mode():
+            tr = self.M.medusa_greedy_search(self.w, self.cfg, self.enc, self.prompt, self.gp, "fp32", max_iters=max_iters)
+        dt = time.perf_counter() - t0
+        return len(tr.sequences) - len(self.prompt), tr.iters, dt
+
+
+def golden_tokens(args, regime: str):
+    """Token ids of stream 0 from the committed fixture of exactly this workload (None when there is none)."""
+    if not (args.preset == "large-v2" and args.heads_type == "base_head" and args.seconds == 30.0):
+        return None
+    name = {("realistic", 10): "large_linear_k10_mixed"}.get((regime, args.heads))
+    if name is None:
+        return None
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    if not os.path.isfile(path):
+        return None
+    return np.load(path)["tokens"].tolist()
+
+
+def run_streams(model, clips, idx, language, alpha, max_iters=0):
+    """Run clips[idx] through generate_from_pcm; returns per-call traces and the wall time."""
+    traces, outs = [], []
+    t0 = time.perf_counter()
+    for i in idx:
+        out = model.generate_from_pcm(clips[i], language=language, exponential_decay_length_penalty=PENALTY,
+                                      posterior_alpha=alpha, max_iters=max_iters)      # H2D of PCM + D2H of ids inside
+        outs.append(out.cpu()[0].tolist())
+        traces.append(model.last_trace)
+    return traces, outs, time.perf_counter() - t0
+
+
+def summarize(cfg, traces, peak):
+    toks = sum(t.n_new_tokens for t in traces)
+    iters = sum(t.iterations for t in traces)
+    dec_ms = sum(t.ms_decode for t in traces)
+    n_sum = sum(0.5 * len(t.sequences) * t.iterations for t in traces)
+    sweeps_a = sum(1 + sum(1 for a in t.accept_lengths[:-1] if a == 0) for t in traces)
+    hist = np.bincount(np.concatenate([np.array(t.accept_lengths, dtype=np.int64) for t in traces]),
+                       minlength=cfg.medusa_num_heads + 1).tolist()
+    b_eng, b_ref = algorithmic_bytes(cfg, iters, sweeps_a, n_sum / max(1, iters))
+    achieved = b_eng / (dec_ms / 1e3) / 1e9
+    return {"tokens": toks, "iterations": iters, "ms_decode": dec_ms, "tokens_per_s": toks / (dec_ms / 1e3),
+            "ms_per_iteration": dec_ms / max(1, iters), "tokens_per_iteration": toks / max(1, iters),
+            "mean_accept": float(np.dot(hist, np.arange(len(hist))) / max(1, sum(hist))), "accept_hist": hist,
+            "two_sweep_iterations": sweeps_a - len(traces), "achieved_gbs": achieved, "frac": achieved / peak,
+            "bytes_eng": b_eng, "bytes_ref": b_ref, "n_sum": n_sum, "sweeps_a": sweeps_a}
 
 
 def main():
@@ -181,8 +231,11 @@ def main():
     ap.add_argument("--heads", type=int, default=10)
     ap.add_argument("--heads-type", default="base_head", choices=["base_head", "medusa_block"])
     ap.add_argument("--seconds", type=float, default=30.0)
-    ap.add_argument("--cpu-iters", type=int, default=8, help="speculative iterations of the CPU baseline sample")
+    ap.add_argument("--regime", default="realistic", choices=sorted(REGIMES))
+    ap.add_argument("--cpu-iters", type=int, default=6, help="speculative iterations per step of the CPU arm / baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other regimes and the K sweep")
+    ap.add_argument("--dump-tokens", default=None, help="write this rank's token lists (JSON) to PATH.rank<r>")
     args = ap.parse_args()
 
     from whisper_medusa_b200.synthetic import preset_config, synthetic_audio, synthetic_state_dict
@@ -191,37 +244,43 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg = preset_config(args.preset, heads=args.heads, heads_type=args.heads_type)
+    alpha = REGIMES[args.regime]
     workload = (f"whisper-{args.preset} + {args.heads} Medusa-{'Block' if cfg.is_block else 'Linear'} heads, batch 1, "
-                f"{args.seconds:g} s synthetic 16 kHz audio per stream, greedy/typical acceptance, max_length 448")
-    config = {"workload": workload, "streams_per_step": world, "parallelism": f"replicas x{world} (independent streams)",
-              "weights": "seeded synthetic fp16 (seed 0)", "l2": "weights (3.1 GB) >> L2: every iteration re-streams them from HBM"}
-    threads = pick_threads(cfg) if (args.impl == "reference" or not args.no_cpu_baseline) else (os.cpu_count() or 1)
+                f"{args.seconds:g} s synthetic 16 kHz audio per stream, typical acceptance, language=en, "
+                f"exponential_decay_length_penalty={PENALTY}, max_length 448")
+    # identical in both arms (the driver compares the two `config` objects)
+    config = {"workload": workload, "acceptance_regime": f"{args.regime} (posterior_alpha={alpha:g})",
+              "streams_per_step": world, "parallelism": f"replicas x{world} (independent streams)",
+              "weights": "seeded synthetic fp16 (seed 0)",
+              "l2": "weights (3.1 GB) >> L2 (126 MB): every iteration re-streams them from HBM"}
+    threads = cpu_threads()
 
     # ------------------------------------------------------------------ reference arm (CPU oracle)
     if args.impl == "reference":
         if rank != 0:
             return
         sd = synthetic_state_dict(cfg, seed=0)
-        vals, per_step = [], []
+        ref = CpuReference(cfg, sd, synthetic_audio(args.seconds, stream_id=0), threads, alpha)
+        tok = iters = 0
+        per_step = []
         for i in range(args.warmup + args.steps):
-            pcm = synthetic_audio(args.seconds, stream_id=i)
-            t0 = time.perf_counter()
-            r = cpu_reference_sample(cfg, sd, pcm, args.cpu_iters, threads)
+            n, it, dt = ref.step(args.cpu_iters)
             if i >= args.warmup:
-                per_step.append(time.perf_counter() - t0)
-                vals.append(r)
-        tok = sum(v["tokens"] for v in vals)
-        dec = sum(v["s_decode"] for v in vals)
-        e2e = tok / sum(per_step)
-        sample = (f"per step: 1 clip, log-mel + full encoder + first {args.cpu_iters} speculative iterations "
-                  f"({vals[0]['tokens']} tokens) of the same workload")
+                tok += n
+                iters += it
+                per_step.append(dt)
+        value = tok / sum(per_step)
+        sample = (f"per step: the first {args.cpu_iters} speculative iterations ({tok // max(1, args.steps)} tokens) of stream 0 of "
+                  f"the same workload, decode loop only, encoder output resident in RAM (log-mel {ref.s_mel:.2f} s + "
+                  f"encoder {ref.s_encoder:.2f} s measured once, NOT included: the ratio against it is conservative)")
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": tok / dec, "unit": "tokens/s", "n_gpus": args.gpus,
+            "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(per_step) / len(per_step),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": config,
-            "cpu_baseline": {"value": tok / dec, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "detail": {"tokens_per_iteration": tok / max(1, iters), "s_mel": ref.s_mel, "s_encoder": ref.s_encoder},
         }))
         return
 
@@ -238,13 +297,16 @@ def main():
     sd = synthetic_state_dict(cfg, seed=0) if (rank == 0 or world == 1) else None
     model = WhisperMedusaModel(cfg, sd)
     model.to(device, broadcast_src=0 if world > 1 else None)   # NCCL broadcast of the packed blob (N > 1)
-    model.set_decode_mode(args.mode)
+    if args.mode != "persistent":
+        model.set_decode_mode(args.mode)                       # (persistent is the engine's default)
 
     def clip(i):
         return torch.from_numpy(synthetic_audio(args.seconds, stream_id=rank + world * i)).pin_memory()
 
-    clips = [clip(i) for i in range(args.warmup + args.steps)]
+    # timed clips first (stream ids rank + world*i, i < steps), warm-up clips after them: stream 0 is always timed
+    clips = [clip(i) for i in range(args.steps + args.warmup)]
     language = "en" if cfg.is_multilingual else None
+    peak, peak_src = measured_peak_gbs()
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -252,40 +314,67 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    for i in range(args.warmup):
-        model.generate_from_pcm(clips[i], language=language)
+    run_streams(model, clips, range(args.steps, args.steps + args.warmup), language, alpha)
     barrier()
-    toks = iters = launches = 0
-    dec_ms = enc_ms = mel_ms = 0.0
-    n_sum = 0.0
-    sweeps_a = 0
     with ClockSampler(local_rank) as cs:
-        t0 = time.perf_counter()
-        for i in range(args.warmup, args.warmup + args.steps):
-            out = model.generate_from_pcm(clips[i], language=language)      # H2D of PCM + D2H of ids inside
-            _ = out.cpu()
-            tr = model.last_trace
-            toks += tr.n_new_tokens
-            iters += tr.iterations
-            dec_ms += tr.ms_decode
-            enc_ms += tr.ms_encoder
-            mel_ms += tr.ms_mel
-            launches += tr.launches_encode + tr.launches_decode
-            n_sum += 0.5 * len(tr.sequences) * tr.iterations   # mean self-KV length over the run ~ L_final / 2
-            sweeps_a += 1 + sum(1 for a in tr.accept_lengths[:-1] if a == 0)   # prompt + one per accept-0 iteration
+        traces, outs, _ = run_streams(model, clips, range(args.steps), language, alpha)
+        barrier_t0 = time.perf_counter()
         barrier()
-        wall = time.perf_counter() - t0
+        wall = _ + (time.perf_counter() - barrier_t0)
     clocks = cs.summary()
+    sm = summarize(cfg, traces, peak)
+    launches = sum(t.launches_encode + t.launches_decode for t in traces)
+    enc_ms = sum(t.ms_encoder for t in traces)
+    mel_ms = sum(t.ms_mel for t in traces)
 
-    stats = torch.tensor([toks, iters, dec_ms, wall, enc_ms, mel_ms, launches, n_sum, sweeps_a], dtype=torch.float64, device=device)
+    # output validation: stream 0 (rank 0, first timed clip) against the committed golden of this workload
+    gold = golden_tokens(args, args.regime) if rank == 0 else None
+    validated = None
+    if gold is not None:
+        if outs[0] != gold:
+            raise SystemExit(f"bench: tokens of stream 0 differ from tests/golden (len {len(outs[0])} vs {len(gold)})")
+        validated = "stream 0 == tests/golden/large_linear_k10_mixed.npz (%d tokens)" % len(gold)
+    if args.dump_tokens:
+        with open(f"{args.dump_tokens}.rank{rank}", "w") as f:
+            json.dump({"stream_ids": [rank + world * i for i in range(args.steps)], "tokens": outs}, f)
+
+    stats = torch.tensor([sm["tokens"], sm["iterations"], sm["ms_decode"], wall, enc_ms, mel_ms, launches], dtype=torch.float64, device=device)
     if dist is not None:
         allv = [torch.zeros_like(stats) for _ in range(world)]
         dist.all_gather(allv, stats)
         allv = torch.stack(allv).cpu()
     else:
         allv = stats.cpu()[None]
+
+    # ---- extras (rank 0, after the headline measurement): other regimes, K sweep --------------------------------------
+    regimes, k_sweep = {}, {}
+    if rank == 0 and not args.no_extras:
+        for name, a in REGIMES.items():
+            if name == args.regime:
+                continue
+            run_streams(model, clips, [args.steps], language, a, max_iters=4)            # warm the regime's path
+            tr2, _, _ = run_streams(model, clips, range(min(2, args.steps)), language, a)
+            s2 = summarize(cfg, tr2, peak)
+            regimes[name] = {k: s2[k] for k in ("tokens_per_s", "ms_per_iteration", "tokens_per_iteration", "mean_accept",
+                                                "accept_hist", "two_sweep_iterations", "frac")}
+            regimes[name]["posterior_alpha"] = a
+        if sd is not None and not cfg.is_block and args.preset == "large-v2":
+            k_sweep[str(args.heads)] = {k: sm[k] for k in ("tokens_per_s", "ms_per_iteration", "tokens_per_iteration", "mean_accept")}
+            for K in (2, 4, 6):
+                if K >= args.heads:
+                    continue
+                # heads are drawn last and in order: the K-head checkpoint of this seed is a prefix of the K=10 one
+                cK = preset_config(args.preset, heads=K, heads_type=args.heads_type)
+                sdK = {k: v for k, v in sd.items() if not k.startswith("medusa_heads.") or int(k.split(".")[1]) <= K}
+                mK = WhisperMedusaModel(cK, sdK).to(device)
+                run_streams(mK, clips, [args.steps], language, alpha, max_iters=4)
+                trK, _, _ = run_streams(mK, clips, range(min(2, args.steps)), language, alpha)
+                sK = summarize(cK, trK, peak)
+                k_sweep[str(K)] = {k: sK[k] for k in ("tokens_per_s", "ms_per_iteration", "tokens_per_iteration", "mean_accept", "frac")}
+                mK.close()
     if rank != 0:
         if dist is not None:
+            dist.barrier()
             dist.destroy_process_group()
         return
     tot_tok = float(allv[:, 0].sum())
@@ -294,48 +383,47 @@ def main():
     max_wall = float(allv[:, 3].max())
     value = tot_tok / (max_dec_ms / 1e3)
     e2e_value = tot_tok / max_wall
-    # roofline of the decode iteration (the dominant kernel: one launch per iteration in persistent mode)
-    it0, n_mean = float(allv[0, 1]), float(allv[0, 7]) / max(1.0, float(allv[0, 1]))
-    bytes_eng, bytes_ref = algorithmic_bytes(cfg, int(it0), int(allv[0, 8]), n_mean)
-    if args.mode == "graph":
-        pass  # same schedule; the graph mode only differs in how stages are launched
-    ms_iter = float(allv[0, 2]) / max(1.0, it0)
-    achieved = bytes_eng / (float(allv[0, 2]) / 1e3) / 1e9
-    peak, peak_src = measured_peak_gbs()
     tok_iter = tot_tok / max(1.0, tot_iter)
-    ref_roofline_tok_s = peak * 1e9 / (bytes_ref / max(1.0, it0)) * tok_iter   # per GPU
+    ref_roofline_tok_s = peak * 1e9 / (sm["bytes_ref"] / max(1, sm["iterations"])) * tok_iter   # per GPU
     result = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * max_wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp16 weights+KV / fp32 accumulate", "data": "synthetic", "config": dict(config, decode_mode=args.mode),
+        "dtype": "fp16 weights+KV / fp32 accumulate", "data": "synthetic", "config": config,
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 480000 * 4,
                 "d2h_bytes_per_step": int(4 * tot_tok / max(1, world * args.steps)) + 16 * 4},
         "gpu_launches": int(allv[:, 6].sum()),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm", "achieved": sm["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": sm["frac"],
                      "traffic": ncu_traffic_bytes(args), "peak_source": peak_src,
                      "kernel": "dec_iteration_ring_kernel (one launch = one speculative iteration)"
                      if args.mode == "persistent" else f"decode iteration ({args.mode})",
-                     "algorithmic_bytes_per_iteration": bytes_eng / max(1.0, it0), "ms_per_iteration": ms_iter,
-                     "reference_schedule_bytes_per_iteration": bytes_ref / max(1.0, it0),
+                     "algorithmic_bytes_per_iteration": sm["bytes_eng"] / max(1, sm["iterations"]),
+                     "ms_per_iteration": sm["ms_per_iteration"],
+                     "reference_schedule_bytes_per_iteration": sm["bytes_ref"] / max(1, sm["iterations"]),
                      "frac_of_reference_schedule_roofline": (value / world) / ref_roofline_tok_s},
-        "detail": {"tokens_per_step": tot_tok / (world * args.steps), "iterations_per_step": tot_iter / (world * args.steps),
-                   "tokens_per_iteration": tot_tok / max(1.0, tot_iter), "ms_mel": float(allv[0, 5]) / args.steps,
-                   "ms_encoder": float(allv[0, 4]) / args.steps, "ms_decode": float(allv[0, 2]) / args.steps},
+        "detail": {"decode_mode": args.mode, "tokens_per_step": tot_tok / (world * args.steps),
+                   "iterations_per_step": tot_iter / (world * args.steps), "tokens_per_iteration": tok_iter,
+                   "mean_accept": sm["mean_accept"], "accept_hist": sm["accept_hist"],
+                   "two_sweep_iterations": sm["two_sweep_iterations"],
+                   "ms_mel": float(allv[0, 5]) / args.steps, "ms_encoder": float(allv[0, 4]) / args.steps,
+                   "ms_decode": float(allv[0, 2]) / args.steps, "validated": validated,
+                   "regimes": regimes, "k_sweep": k_sweep},
     }
-    if not args.no_cpu_baseline and world >= 1:
+    if not args.no_cpu_baseline:
         try:
             if sd is None:
                 sd = synthetic_state_dict(cfg, seed=0)
-            r = cpu_reference_sample(cfg, sd, clips[0].numpy(), args.cpu_iters, threads)
+            ref = CpuReference(cfg, sd, clips[0].numpy(), threads, alpha)
+            n, it, dt = ref.step(args.cpu_iters)
             result["cpu_baseline"] = {
-                "value": r["tok_s_decode"], "unit": "tokens/s", "cores": threads, "kind": "port",
-                "sample": (f"1 clip: log-mel {r['s_mel']:.2f}s + encoder {r['s_encoder']:.2f}s + first {r['iters']} "
-                           f"speculative iterations ({r['tokens']} tokens) in {r['s_decode']:.2f}s; e2e {r['tok_s_e2e']:.1f} tok/s")}
+                "value": n / dt, "unit": "tokens/s", "cores": threads, "kind": "port",
+                "sample": (f"stream 0: first {it} speculative iterations ({n} tokens) of the decode loop in {dt:.2f} s, encoder "
+                           f"output resident (log-mel {ref.s_mel:.2f} s + encoder {ref.s_encoder:.2f} s, not included)")}
         except Exception as e:  # noqa: BLE001
             result["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(result))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -96,6 +96,10 @@ int wm_set_suppress(wm_handle* h, const int32_t* suppress_ids, int32_t n_suppres
 int wm_encode_pcm(wm_handle* h, const float* pcm, int32_t n_samples);
 /* f32 log-mel [n_mels][3000] on the host (what WhisperProcessor produces). */
 int wm_encode_mel(wm_handle* h, const float* mel);
+/* The same features already in DEVICE memory of the handle's GPU (a CUDA `input_features` tensor: the
+ * reference's caller does `input_features.to(device)` first, README.md:129-133).  `producer_stream` is the
+ * cudaStream_t (NULL = legacy default stream) the features were produced on: the copy is ordered after it. */
+int wm_encode_mel_device(wm_handle* h, const float* mel_dev, void* producer_stream);
 
 /* ---- the speculative decode loop (model.py:404-835 + medusa_utils.py:424-671) ---------- */
 /* prompt: decoder_input_ids.  out_ids receives the FULL sequence (prompt + generated, after
@@ -103,6 +107,11 @@ int wm_encode_mel(wm_handle* h, const float* mel);
  * accept_lens (capacity >= max_length, may be NULL) receives the per-iteration accept length. */
 int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt, const wm_gen_params* gp,
                 int32_t* out_ids, int32_t* n_out, int32_t* accept_lens, int32_t* n_iter);
+
+/* ---- teacher-forced forward (model.py:1223-1347 `forward(...).logits`, shape [K+1, 1, T, V]) -------------- */
+/* ids: 1..16 decoder_input_ids; out (host, capacity (K+1) * n_ids * vocab_size floats) receives the raw logits of
+ * every head at every position, out[(k * n_ids + t) * V + v]; k = 0 is the base head.  Needs wm_encode_* first. */
+int wm_forward(wm_handle* h, const int32_t* ids, int32_t n_ids, float* out);
 
 /* ---- parity taps / measurements --------------------------------------------------------- */
 int wm_get_mel(wm_handle* h, float* out /* [n_mels][3000] */);
@@ -115,10 +124,10 @@ int wm_last_logits(wm_handle* h, int32_t which, float* out);
 double wm_last_ms(wm_handle* h, int32_t what);
 /* Number of kernel launches issued by the last wm_encode_* (what=1) / wm_generate (what=2). */
 int64_t wm_last_launches(wm_handle* h, int32_t what);
-/* Decode execution mode: 0 = CUDA graphs of stage kernels (debug / per-stage profiling), 1 =
- * persistent cooperative kernel per speculative iteration (grid barriers only), 2 = the same with
- * the shared-memory weight ring (bulk-async prefetch across barriers; the product path).
- * Returns the previous mode. */
+/* Decode execution mode: 2 (DEFAULT) = one persistent cooperative kernel per speculative iteration with the
+ * shared-memory weight ring (bulk-async prefetch across barriers; the product path); 1 = the same without the
+ * ring (grid barriers only); 0 = CUDA graphs of stage kernels (debug / per-stage profiling, and the automatic
+ * default for a decoder width the ring kernel is not instantiated for).  Returns the previous mode. */
 int wm_set_decode_mode(wm_handle* h, int32_t mode);
 /* Engine options: "decode_mode" (as above); "enc_gemm" 1 = tcgen05/TMA/TMEM encoder GEMM (default),
  * 0 = mma.sync encoder GEMM (cross-check); "profile" 1 = record the stage timeline below. */

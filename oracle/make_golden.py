@@ -26,7 +26,12 @@ from whisper_medusa_b200.synthetic import preset_config, synthetic_audio, synthe
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-# name -> (preset, heads, heads_type, weight seed, audio seconds, stream id, max_length, penalty, medusa temperature)
+# name -> (preset, heads, heads_type, weight seed, audio seconds, stream id, max_length, penalty, medusa temperature
+#          [, posterior_alpha, posterior_threshold])
+# The synthetic large-v2 model accepts every candidate under the default typical-acceptance constants (flat
+# posteriors: p_candidate * e^H ~ 200-300 against alpha = 0.3).  ``posterior_alpha`` -- a generation-config field of
+# the reference (medusa_utils.py:14-18) -- is the acceptance knob: alpha = 100 fails the weaker chain positions, which
+# gives mixed accept lengths.
 CASES = {
     "micro_linear_k4": ("micro", 4, "base_head", 2, 5.0, 0, 120, None, 1.0),
     "micro_block_k10": ("micro", 10, "medusa_block", 9, 5.0, 1, 120, None, 1.0),
@@ -35,6 +40,16 @@ CASES = {
     "tiny_block_k4": ("tiny.en", 4, "medusa_block", 1, 5.0, 0, 200, None, 1.0),
     "large_linear_k10": ("large-v2", 10, "base_head", 0, 30.0, 0, 448, None, 1.0),
     "large_block_k10": ("large-v2", 10, "medusa_block", 0, 30.0, 0, 120, None, 1.0),   # short budget: ~10 iterations
+    # mixed accept lengths + the length penalty of the reference's eval script (eval_whisper_medusa.py:61-65) + EOS stop
+    "large_linear_k10_mixed": ("large-v2", 10, "base_head", 0, 30.0, 0, 448, (140, 1.01), 1.0, 100.0, 0.09),
+    "large_linear_k6_mixed": ("large-v2", 6, "base_head", 0, 30.0, 1, 130, None, 1.0, 100.0, 0.09),
+    "large_linear_k4_mixed": ("large-v2", 4, "base_head", 0, 30.0, 2, 110, None, 1.0, 100.0, 0.09),
+    "large_linear_k2_mixed": ("large-v2", 2, "base_head", 0, 30.0, 3, 90, None, 1.0, 100.0, 0.09),
+    # alpha = 230 also fails the first chain position about half of the time: accept-0 iterations (two emitted
+    # tokens, the extra one-token sweep) interleaved with accepting ones
+    # (stream 5 of a small search over streams 4-7 x alpha 210/230/250: the only one with accept-0 iterations whose
+    # tightest acceptance comparison is still 2.4e-3 away from its threshold)
+    "large_linear_k10_a0mix": ("large-v2", 10, "base_head", 0, 30.0, 5, 150, None, 1.0, 230.0, 0.09),
 }
 
 TOPN = 16
@@ -46,7 +61,8 @@ def _topn(rows: torch.Tensor):
 
 
 def make_case(name: str) -> dict:
-    preset, heads, htype, seed, secs, stream, max_len, pen, temp = CASES[name]
+    preset, heads, htype, seed, secs, stream, max_len, pen, temp = CASES[name][:9]
+    alpha, thr = (CASES[name][9:] + (0.3, 0.09))[:2] if len(CASES[name]) > 9 else (0.3, 0.09)
     cfg = preset_config(preset, heads=heads, heads_type=htype)
     t0 = time.time()
     sd = synthetic_state_dict(cfg, seed=seed)
@@ -56,7 +72,7 @@ def make_case(name: str) -> dict:
     melt = torch.from_numpy(mel)
     language = "en" if cfg.is_multilingual else None
     prompt = M.init_tokens(cfg, language)
-    gp = M.gen_params(cfg, prompt, pen, max_len, temperature=temp)
+    gp = M.gen_params(cfg, prompt, pen, max_len, temperature=temp, posterior_alpha=alpha, posterior_threshold=thr)
     out = {}
     for regime in ("engine", "fp32"):
         enc = W.encoder_forward(w, cfg, melt, regime)
@@ -84,6 +100,7 @@ def make_case(name: str) -> dict:
     out["meta"] = np.array([seed, stream, max_len, heads, int(htype == "medusa_block")], dtype=np.int64)
     out["audio_seconds"] = np.float32(secs)
     out["temperature"] = np.float32(temp)
+    out["posterior"] = np.array([alpha, thr], dtype=np.float64)
     out["penalty"] = np.array(pen if pen is not None else (-1, 1.0), dtype=np.float64)
     return out
 

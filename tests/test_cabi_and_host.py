@@ -201,12 +201,36 @@ def test_generate_argument_errors_match_reference():
             m.generate(torch.zeros(1, 80, 6000))                          # model.py:1213
         with pytest.raises(Exception):
             m.generate(torch.zeros(1, 80, 3000), num_beams=4)             # model.py:1153
+        # options the reference takes but this path cannot honour fail loudly instead of being dropped
+        with pytest.raises(NotImplementedError):
+            m.generate(torch.zeros(1, 80, 3000), temperature=0.4)         # -> do_sample (model.py:1878-1881): no sampling branch
+        with pytest.raises(NotImplementedError):
+            m.generate(torch.zeros(1, 80, 3000), temperature=(0.0, 0.2, 0.4))
+        with pytest.raises(NotImplementedError):
+            m.generate(torch.zeros(1, 80, 3000), do_sample=True)
+        with pytest.raises(NotImplementedError):
+            m.generate(torch.zeros(1, 80, 3000), repetition_penalty=1.2)
     finally:
         m._handle = None
     big = WhisperMedusaModel(preset_config("large-v2", heads=10), None)
     assert big._init_tokens("en", None) == [50258, 50259, 50359, 50363]
-    with pytest.raises(NotImplementedError):
-        big._init_tokens(None, None)
+    assert big._init_tokens("german", "translate") == [50258, 50261, 50358, 50363]   # names as HF accepts them
+    assert big._init_tokens("<|ja|>", None)[1] == 50266
+    with pytest.raises(ValueError):
+        big._init_tokens("klingon", None)
     small = WhisperMedusaModel(preset_config("tiny.en", heads=4), None)
     assert small._init_tokens(None, None) == [50257, 50362]
     assert WhisperMedusaModel._strip([1, 2, 5, 6, 9, 9], 2, 9, 9) == [5, 6]
+
+
+def test_language_tables_match_the_installed_transformers():
+    """The embedded Whisper language table (config.py) against transformers' own (tokenization_whisper.py)."""
+    tw = pytest.importorskip("transformers.models.whisper.tokenization_whisper")
+    from whisper_medusa_b200.config import WHISPER_LANGUAGE_CODES, WHISPER_LANGUAGE_NAMES, WHISPER_PRESETS, language_token
+
+    codes = list(tw.LANGUAGES.keys())
+    assert codes[:99] == WHISPER_LANGUAGE_CODES          # (large-v3 appended "yue"; v2 checkpoints have 99)
+    assert {k: v for k, v in tw.TO_LANGUAGE_CODE.items()} == WHISPER_LANGUAGE_NAMES
+    lang = WHISPER_PRESETS["openai/whisper-large-v2"]["lang_to_id"]
+    assert lang["<|en|>"] == 50259 and lang["<|su|>"] == 50357 and len(lang) == 99
+    assert language_token("English") == "<|en|>" and language_token("fr") == "<|fr|>"

@@ -47,8 +47,10 @@ SYMBOLS = {
     "wm_set_suppress": (C.c_int, [C.c_void_p, _P(C.c_int32), C.c_int32, _P(C.c_int32), C.c_int32]),
     "wm_encode_pcm": (C.c_int, [C.c_void_p, _P(C.c_float), C.c_int32]),
     "wm_encode_mel": (C.c_int, [C.c_void_p, _P(C.c_float)]),
+    "wm_encode_mel_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "wm_generate": (C.c_int, [C.c_void_p, _P(C.c_int32), C.c_int32, _P(WmGenParams), _P(C.c_int32),
                               _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]),
+    "wm_forward": (C.c_int, [C.c_void_p, _P(C.c_int32), C.c_int32, _P(C.c_float)]),
     "wm_get_mel": (C.c_int, [C.c_void_p, _P(C.c_float)]),
     "wm_get_encoder_out": (C.c_int, [C.c_void_p, _P(C.c_float)]),
     "wm_last_logits": (C.c_int, [C.c_void_p, C.c_int32, _P(C.c_float)]),

@@ -40,6 +40,47 @@ _SUPPRESS_EN = [
     34949, 40283, 40493, 40549, 47282, 49146, 50257, 50357, 50358, 50359, 50360, 50361,
 ]
 
+#: Whisper's language codes in token order (openai/whisper ``tokenizer.py`` LANGUAGES; multilingual checkpoints up to
+#: large-v2 number them 50259 + index) and the spoken names HF's ``generate(language=...)`` also accepts
+#: (``tokenization_whisper.py`` TO_LANGUAGE_CODE).  tests/test_cabi_and_host.py compares both with the installed
+#: transformers tables.
+WHISPER_LANGUAGE_CODES = (
+    "en zh de es ru ko fr ja pt tr pl ca nl ar sv it id hi fi vi he uk el ms cs ro da hu ta no th ur hr bg lt la mi ml cy "
+    "sk te fa lv bn sr az sl kn et mk br eu is hy ne mn bs kk sq sw gl mr pa si km sn yo so af oc ka be tg sd gu am yi lo "
+    "uz fo ht ps tk nn mt sa lb my bo tl mg as tt haw ln ha ba jw su").split()
+WHISPER_LANGUAGE_NAMES = {
+    "english": "en", "chinese": "zh", "german": "de", "spanish": "es", "russian": "ru", "korean": "ko", "french": "fr",
+    "japanese": "ja", "portuguese": "pt", "turkish": "tr", "polish": "pl", "catalan": "ca", "dutch": "nl", "arabic": "ar",
+    "swedish": "sv", "italian": "it", "indonesian": "id", "hindi": "hi", "finnish": "fi", "vietnamese": "vi",
+    "hebrew": "he", "ukrainian": "uk", "greek": "el", "malay": "ms", "czech": "cs", "romanian": "ro", "danish": "da",
+    "hungarian": "hu", "tamil": "ta", "norwegian": "no", "thai": "th", "urdu": "ur", "croatian": "hr", "bulgarian": "bg",
+    "lithuanian": "lt", "latin": "la", "maori": "mi", "malayalam": "ml", "welsh": "cy", "slovak": "sk", "telugu": "te",
+    "persian": "fa", "latvian": "lv", "bengali": "bn", "serbian": "sr", "azerbaijani": "az", "slovenian": "sl",
+    "kannada": "kn", "estonian": "et", "macedonian": "mk", "breton": "br", "basque": "eu", "icelandic": "is",
+    "armenian": "hy", "nepali": "ne", "mongolian": "mn", "bosnian": "bs", "kazakh": "kk", "albanian": "sq",
+    "swahili": "sw", "galician": "gl", "marathi": "mr", "punjabi": "pa", "sinhala": "si", "khmer": "km", "shona": "sn",
+    "yoruba": "yo", "somali": "so", "afrikaans": "af", "occitan": "oc", "georgian": "ka", "belarusian": "be",
+    "tajik": "tg", "sindhi": "sd", "gujarati": "gu", "amharic": "am", "yiddish": "yi", "lao": "lo", "uzbek": "uz",
+    "faroese": "fo", "haitian creole": "ht", "pashto": "ps", "turkmen": "tk", "nynorsk": "nn", "maltese": "mt",
+    "sanskrit": "sa", "luxembourgish": "lb", "myanmar": "my", "tibetan": "bo", "tagalog": "tl", "malagasy": "mg",
+    "assamese": "as", "tatar": "tt", "hawaiian": "haw", "lingala": "ln", "hausa": "ha", "bashkir": "ba",
+    "javanese": "jw", "sundanese": "su", "burmese": "my", "valencian": "ca", "flemish": "nl", "haitian": "ht",
+    "letzeburgesch": "lb", "pushto": "ps", "panjabi": "pa", "moldavian": "ro", "moldovan": "ro", "sinhalese": "si",
+    "castilian": "es", "mandarin": "zh", "cantonese": "yue",
+}
+
+
+def language_token(language: str) -> str:
+    """``"en"`` / ``"english"`` / ``"<|en|>"`` -> ``"<|en|>"`` (HF ``generation_whisper.py:1490-1520``)."""
+    lang = language.lower()
+    if lang.startswith("<|") and lang.endswith("|>"):
+        return lang
+    lang = WHISPER_LANGUAGE_NAMES.get(lang, lang)
+    return f"<|{lang}|>"
+
+
+_LANG_TO_ID_V2 = {f"<|{c}|>": 50259 + i for i, c in enumerate(WHISPER_LANGUAGE_CODES)}
+
 #: Whisper dimensions per base model name (SURVEY.md section 2.1).  ``micro`` is a
 #: test-only shape small enough for pure-Python oracle loops.
 WHISPER_PRESETS: Dict[str, Dict[str, Any]] = {
@@ -52,7 +93,7 @@ WHISPER_PRESETS: Dict[str, Dict[str, Any]] = {
         decoder_start_token_id=50258, is_multilingual=True,
         suppress_tokens=_SUPPRESS_MULTILINGUAL, begin_suppress_tokens=[220, 50257],
         # <|startoftranscript|> <|en|> <|transcribe|> <|notimestamps|>  
-        lang_to_id={"<|en|>": 50259}, task_to_id={"transcribe": 50359, "translate": 50358},
+        lang_to_id=_LANG_TO_ID_V2, task_to_id={"transcribe": 50359, "translate": 50358},
         no_timestamps_token_id=50363, max_length=448,
     ),
     "openai/whisper-tiny.en": dict(

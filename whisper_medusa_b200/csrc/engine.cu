@@ -77,6 +77,8 @@ struct wm_handle {
   // pinned staging + timing
   int* h_state = nullptr;  // pinned copy of the DecState header
   float* h_stage = nullptr;  // pinned staging for pcm / mel
+  DecState* h_init = nullptr;  // pinned initial loop state (uploaded asynchronously by wm_generate)
+  float* h_pen = nullptr;      // pinned EOS-penalty table
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double ms[3] = {0, 0, 0};
   int64_t launches[3] = {0, 0, 0};
@@ -292,6 +294,8 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   m.st = h->st; m.tok_mask = h->tok_mask; m.pen_tab = h->pen_tab; m.bar = h->bar;
   CK(cudaMallocHost((void**)&h->h_state, 64 * sizeof(int)));
   CK(cudaMallocHost((void**)&h->h_stage, (size_t)kSamples * sizeof(float)));
+  CK(cudaMallocHost((void**)&h->h_init, sizeof(DecState)));
+  CK(cudaMallocHost((void**)&h->h_pen, (size_t)(WM_MAX_POS + 32) * sizeof(float)));
 
   h->hi.n_sm = h->n_sm; h->hi.H = c.n_heads; h->hi.K = c.medusa_num_heads; h->hi.n_layers = c.dec_layers;
   h->hi.has_block = m.has_block;
@@ -299,6 +303,9 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   h->hi.smem = dec_smem_bytes((int)d, (int)f);
   h->hi.smem_ring = dec_ring_smem_bytes((int)d);
   CK(dec_configure((int)d, h->hi.smem, h->hi.smem_ring));
+  // product path by default: one persistent ring-kernel launch per speculative iteration.  Decoder widths the ring
+  // kernel is not instantiated for (WM_RING_WIDTHS) fall back to the stage-kernel graphs.
+  h->decode_mode = h->hi.smem_ring ? 2 : 0;
   {
     std::vector<int> flat;
     dec_build_program(c.dec_layers, m.has_block, flat, m.prog_off);
@@ -338,6 +345,8 @@ extern "C" int wm_destroy(wm_handle* h) {
   if (h->wowned) F(h->wdev);
   if (h->h_state) cudaFreeHost(h->h_state);
   if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->h_init) cudaFreeHost(h->h_init);
+  if (h->h_pen) cudaFreeHost(h->h_pen);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -548,6 +557,23 @@ extern "C" int wm_encode_pcm(wm_handle* h, const float* pcm, int32_t n) {
   return finish_encode(h);
 }
 
+extern "C" int wm_encode_mel_device(wm_handle* h, const float* mel_dev, void* producer_stream) {
+  if (!h || !mel_dev) return WM_ERR_INVALID;
+  if (!h->wready) return fail(h, WM_ERR_STATE, "weights not loaded");
+  CK(cudaSetDevice(h->device));
+  h->launches[0] = h->launches[1] = 0;
+  // order after the work that produced the features on the caller's stream
+  CK(cudaEventRecord(h->ev[5], reinterpret_cast<cudaStream_t>(producer_stream)));
+  CK(cudaStreamWaitEvent(h->stream, h->ev[5], 0));
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  CK(cudaMemcpyAsync(h->mel32, mel_dev, (size_t)80 * kFrames * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  CK(mel_to_time_major(h->mel32, h->x_tm, h->stream, &h->launches[0]));
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  int r = run_encoder(h);
+  if (r != WM_OK) return r;
+  return finish_encode(h);
+}
+
 extern "C" int wm_encode_mel(wm_handle* h, const float* mel) {
   if (!h || !mel) return WM_ERR_INVALID;
   if (!h->wready) return fail(h, WM_ERR_STATE, "weights not loaded");
@@ -606,19 +632,20 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
 
   // EOS exponential-decay penalty table (HF logits_process.py:1742-1772): indexed by cur_len
   if (gp->penalty_start != h->last_pen_start || gp->penalty_factor != h->last_pen_factor || n_prompt != h->last_pen_prompt) {
-    std::vector<float> tab(WM_MAX_POS + 32, 0.f);
+    // (pinned staging, stream-ordered upload: the previous call's copy completed before that call returned)
+    const int ntab = WM_MAX_POS + 32;
+    for (int L = 0; L < ntab; ++L) h->h_pen[L] = 0.f;
     if (gp->penalty_start >= 0) {
       const int reg = gp->penalty_start + n_prompt;
-      for (int L = 0; L < (int)tab.size(); ++L)
-        if (L > reg) tab[L] = (float)(std::pow((double)gp->penalty_factor, (double)(L - reg)) - 1.0);
+      for (int L = 0; L < ntab; ++L)
+        if (L > reg) h->h_pen[L] = (float)(std::pow((double)gp->penalty_factor, (double)(L - reg)) - 1.0);
     }
-    CK(cudaMemcpyAsync(h->pen_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpyAsync(h->pen_tab, h->h_pen, (size_t)ntab * sizeof(float), cudaMemcpyHostToDevice, s));
     h->last_pen_start = gp->penalty_start; h->last_pen_factor = gp->penalty_factor; h->last_pen_prompt = n_prompt;
   }
   // loop state
   {
-    static thread_local DecState hs;
+    DecState& hs = *h->h_init;   // pinned: the upload is asynchronous, no host synchronisation before the first launch
     memset(&hs, 0, sizeof hs);
     hs.L = n_prompt; hs.kv_len = 0; hs.done = 0; hs.n_iter = 0; hs.max_iters = gp->max_iters; hs.need_a = 1;
     hs.max_length = gp->max_length; hs.eos = gp->eos_token_id; hs.pad = gp->pad_token_id;
@@ -631,7 +658,6 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
     CK(cudaMemsetAsync(h->bar, 0, 8 * sizeof(unsigned int), s));
     CK(cudaMemsetAsync(h->hm.cross_cnt, 0, (size_t)h->cfg.n_heads * sizeof(unsigned int), s));
     CK(cudaMemsetAsync(h->hm.gemm_cnt, 0, (size_t)h->n_sm * sizeof(unsigned int), s));
-    CK(cudaStreamSynchronize(s));
   }
   cudaGraphExec_t gA1 = nullptr, gAp = nullptr, gT = nullptr, gB = nullptr;
   int64_t nA1 = 0, nAp = 0, nT = 0, nB = 0;
@@ -695,6 +721,44 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
   if (accept_lens && iters > 0)
     CK(cudaMemcpy(accept_lens, reinterpret_cast<const char*>(h->st) + offsetof(DecState, accept_hist),
                   (size_t)iters * sizeof(int), cudaMemcpyDeviceToHost));
+  return WM_OK;
+}
+
+// Stacked head logits of a teacher-forced decoder pass (reference WhisperMedusaModel.forward, model.py:1223-1347:
+// `logits` [K+1, batch 1, T, V]).  The loop kernels only ever need the heads at the LAST position, so this utility
+// entry runs the prefix ids[0..t) through sweep A + the candidate tail for t = 1..T (stage-kernel graphs; O(T^2) rows,
+// T <= 16) and collects the K+1 rows of each: out[(k * T + t) * V + v].  Raw logits, no processors.
+extern "C" int wm_forward(wm_handle* h, const int32_t* ids, int32_t n_ids, float* out) {
+  if (!h || !ids || !out) return WM_ERR_INVALID;
+  if (!h->encoded) return fail(h, WM_ERR_STATE, "wm_encode_* must be called before wm_forward");
+  if (n_ids < 1 || n_ids > WM_MAX_T) return fail(h, WM_ERR_INVALID, "wm_forward takes 1..16 decoder ids");
+  for (int i = 0; i < n_ids; ++i)
+    if (ids[i] < 0 || ids[i] >= h->cfg.vocab_size) return fail(h, WM_ERR_INVALID, "decoder id out of range");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int K = h->cfg.medusa_num_heads;
+  const size_t V = (size_t)h->cfg.vocab_size;
+  for (int t = 1; t <= n_ids; ++t) {
+    DecState& hs = *h->h_init;
+    memset(&hs, 0, sizeof hs);
+    hs.L = t; hs.need_a = 1; hs.max_length = h->cfg.max_target_positions; hs.eos = -1; hs.pad = -1; hs.begin_index = -1;
+    hs.temperature = 1.f; hs.post_thr = 0.09f; hs.post_alpha = 0.3f;
+    for (int i = 0; i < t; ++i) hs.ids[i] = ids[i];
+    CK(cudaMemcpyAsync(h->st, &hs, sizeof hs, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->hm.cross_cnt, 0, (size_t)h->cfg.n_heads * sizeof(unsigned int), s));
+    CK(cudaMemsetAsync(h->hm.gemm_cnt, 0, (size_t)h->n_sm * sizeof(unsigned int), s));
+    cudaGraphExec_t gA = nullptr, gT = nullptr;
+    int64_t nA = 0, nT = 0;
+    int r;
+    if ((r = get_graph(h, 0, t, &gA, &nA)) != WM_OK) return r;
+    if ((r = get_graph(h, 1, 1, &gT, &nT)) != WM_OK) return r;
+    CK(cudaGraphLaunch(gA, s));
+    CK(cudaGraphLaunch(gT, s));
+    for (int k = 0; k <= K; ++k)
+      CK(cudaMemcpyAsync(out + ((size_t)k * n_ids + (t - 1)) * V, h->hm.logits_a + (size_t)k * V, V * sizeof(float),
+                         cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));   // h_init is rewritten by the next prefix
+  }
   return WM_OK;
 }
 

@@ -249,22 +249,35 @@ class WhisperMedusaModel:
         toks = [int(g.decoder_start_token_id)]
         if g.is_multilingual:
             if language is None:
-                raise NotImplementedError(
-                    "language detection (an extra encoder+decoder pass, generation_whisper.py:1559-1566) is not "
-                    "implemented; pass language=... as the reference's README/eval script do")
-            key = language if language.startswith("<|") else f"<|{language}|>"
-            if key not in g.lang_to_id:
-                raise ValueError(f"unsupported language {language!r}; known: {sorted(g.lang_to_id)}")
-            toks.append(int(g.lang_to_id[key]))
+                lang_id = self._detect_language()
+            else:
+                from .config import language_token
+
+                key = language_token(language)
+                if key not in g.lang_to_id:
+                    raise ValueError(f"Unsupported language: {language}. Language should be one of: {sorted(g.lang_to_id)}.")
+                lang_id = int(g.lang_to_id[key])
+            toks.append(lang_id)
             toks.append(int(g.task_to_id[task or "transcribe"]))
         elif language is not None or task is not None:
             raise ValueError("Cannot specify `task` or `language` for an English-only model")
         toks.append(int(g.no_timestamps_token_id))
         return toks
 
-    def _gen_params(self, prompt_len: int, exponential_decay_length_penalty, max_length, temperature,
-                    max_iters) -> _lib.WmGenParams:
+    def _detect_language(self) -> int:
+        """HF ``generation_whisper.py:1559-1566`` / ``detect_language``: one decoder step on ``<|startoftranscript|>``;
+        the language token with the largest base logit wins (all non-language ids masked)."""
         g = self.generation_config
+        lang_ids = sorted(int(v) for v in g.lang_to_id.values())
+        if not lang_ids:
+            raise ValueError("generation_config.lang_to_id is empty: cannot detect the language")
+        logits = self.forward(decoder_input_ids=torch.tensor([[int(g.decoder_start_token_id)]]), disable_medusa=True).logits
+        row = logits[0, 0, -1]
+        return lang_ids[int(torch.argmax(row[torch.tensor(lang_ids)]))]
+
+    def _gen_params(self, prompt_len: int, exponential_decay_length_penalty, max_length, temperature,
+                    max_iters, g=None) -> _lib.WmGenParams:
+        g = g if g is not None else self.generation_config
         pen = exponential_decay_length_penalty if exponential_decay_length_penalty is not None \
             else g.exponential_decay_length_penalty
         return _lib.WmGenParams(
@@ -340,11 +353,39 @@ class WhisperMedusaModel:
                 raise NotImplementedError("custom logits processors / stopping criteria / prompt_ids are not implemented")
         if input_features.shape[-1] != N_FRAMES or input_features.shape[-2] != self.config.num_mel_bins:
             raise ValueError(f"input_features must be [1, {self.config.num_mel_bins}, {N_FRAMES}] (WhisperProcessor output)")
-        mel = input_features.detach().to("cpu", torch.float32).contiguous()
+        self._check_unsupported(temperature, attention_mask, kwargs)
+        self._encode_features(input_features)
+        return self._decode(language, task, kwargs, temperature, generation_config)
+
+    def _encode_features(self, input_features: torch.Tensor) -> None:
         lib = _lib.load()
-        _check(lib, self._handle, lib.wm_encode_mel(self._handle, C.cast(mel.data_ptr(), C.POINTER(C.c_float))),
-               "wm_encode_mel")
-        return self._decode(language, task, kwargs, temperature)
+        if input_features.is_cuda:
+            # device-resident features (the reference's callers do input_features.to(device) first): one
+            # device-to-device copy ordered after the producing stream, no host round trip
+            if input_features.device != self._device:
+                raise EngineError(f"input_features are on {input_features.device}, the engine on {self._device}")
+            mel = input_features.detach().to(torch.float32).contiguous()
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            _check(lib, self._handle, lib.wm_encode_mel_device(self._handle, C.c_void_p(mel.data_ptr()), C.c_void_p(stream)),
+                   "wm_encode_mel_device")
+        else:
+            mel = input_features.detach().to(torch.float32).contiguous()
+            _check(lib, self._handle, lib.wm_encode_mel(self._handle, C.cast(mel.data_ptr(), C.POINTER(C.c_float))),
+                   "wm_encode_mel")
+
+    @staticmethod
+    def _check_unsupported(temperature, attention_mask, kwargs) -> None:
+        """Options the reference accepts but cannot honour on this path fail loudly instead of being dropped."""
+        temps = temperature if isinstance(temperature, (tuple, list)) else (temperature,)
+        if any(t not in (None, 0, 0.0) for t in temps) or kwargs.get("do_sample"):
+            # generate_with_fallback turns temperature > 0 into do_sample=True (model.py:1878-1881), and
+            # _multi_heads_generate has no sampling branch (model.py:1130-1156)
+            raise NotImplementedError("sampling (temperature > 0 / do_sample) is not supported with medusa: greedy search only")
+        known = {"exponential_decay_length_penalty", "max_length", "max_new_tokens", "max_iters", "medusa_temperature",
+                 "posterior_threshold", "posterior_alpha", "num_beams", "do_sample", "use_cache"}
+        unknown = sorted(set(kwargs) - known)
+        if unknown:
+            raise NotImplementedError(f"generate() options not implemented by the B200 engine: {unknown}")
 
     def generate_from_pcm(self, pcm: Union[np.ndarray, torch.Tensor], language: Optional[str] = None,
                           task: Optional[str] = None, temperature=None, **kwargs) -> torch.Tensor:
@@ -358,10 +399,11 @@ class WhisperMedusaModel:
         _check(lib, self._handle,
                lib.wm_encode_pcm(self._handle, C.cast(x.data_ptr(), C.POINTER(C.c_float)), int(x.numel())),
                "wm_encode_pcm")
+        self._check_unsupported(temperature, None, kwargs)
         return self._decode(language, task, kwargs, temperature)
 
-    def _decode(self, language, task, kwargs, temperature) -> torch.Tensor:
-        g = self.generation_config
+    def _decode(self, language, task, kwargs, temperature, generation_config=None) -> torch.Tensor:
+        g = generation_config if generation_config is not None else self.generation_config
         cur = (tuple(g.suppress_tokens or []), tuple(g.begin_suppress_tokens or []))
         if cur != getattr(self, "_pushed", None):
             self._push_suppress()
@@ -369,12 +411,69 @@ class WhisperMedusaModel:
         # generate() always runs the loop with temperature 1.0 => typical acceptance (model.py:1878-1881);
         # `medusa_temperature=0` selects the exact-match branch reachable through _medusa_greedy_search.
         t = kwargs.pop("medusa_temperature", 1.0)
+        max_length = kwargs.pop("max_length", None)
+        if kwargs.get("max_new_tokens") is not None:         # HF: max_length = prompt + max_new_tokens
+            max_length = len(prompt) + int(kwargs.pop("max_new_tokens"))
         gp = self._gen_params(len(prompt), kwargs.pop("exponential_decay_length_penalty", None),
-                              kwargs.pop("max_length", None), t, kwargs.pop("max_iters", 0))
+                              max_length, t, kwargs.pop("max_iters", 0), g)
+        # per-call overrides of the acceptance constants (HF generate(**kwargs) updates the generation config)
+        if kwargs.get("posterior_threshold") is not None:
+            gp.posterior_threshold = float(kwargs.pop("posterior_threshold"))
+        if kwargs.get("posterior_alpha") is not None:
+            gp.posterior_alpha = float(kwargs.pop("posterior_alpha"))
         tr = self._run_loop(prompt, gp)
         self.last_trace = tr
         out = self._strip(tr.sequences, len(prompt), int(gp.pad_token_id), int(gp.eos_token_id))
         return torch.tensor([out], dtype=torch.long, device=self._device)
+
+    # ------------------------------------------------------------------ forward (reference model.py:1223-1347)
+    def forward(self, input_features: Optional[torch.Tensor] = None, attention_mask=None,
+                decoder_input_ids: Optional[torch.Tensor] = None, decoder_attention_mask=None, head_mask=None,
+                decoder_head_mask=None, cross_attn_head_mask=None, encoder_outputs=None, past_key_values=None,
+                decoder_inputs_embeds=None, decoder_position_ids=None, labels=None, use_cache=None,
+                output_attentions=None, output_hidden_states=None, return_dict=None, disable_medusa: bool = False,
+                **kwargs):
+        """Teacher-forced pass: ``.logits`` = stacked head logits ``[K+1, 1, T, V]`` (``disable_medusa`` -> ``[1, 1, T,
+        V]``), T <= 16 decoder ids from an empty cache.  ``input_features`` (host or device) are encoded first; without
+        them the encoder states of the previous ``generate`` / ``forward`` call are reused (the reference's
+        ``encoder_outputs`` argument; tensors cannot be injected into the engine)."""
+        self._require_engine()
+        for name, v in (("labels", labels), ("past_key_values", past_key_values), ("decoder_inputs_embeds", decoder_inputs_embeds),
+                        ("decoder_position_ids", decoder_position_ids), ("decoder_attention_mask", decoder_attention_mask)):
+            if v is not None:
+                raise NotImplementedError(f"forward({name}=...) is not implemented by the inference engine")
+        if decoder_input_ids is None:
+            raise ValueError("decoder_input_ids is required")
+        ids = torch.as_tensor(decoder_input_ids).detach().to("cpu", torch.int32).contiguous()
+        assert ids.dim() == 2 and ids.shape[0] == 1, "Batch size should be 1"
+        if input_features is not None:
+            assert input_features.shape[0] == 1, "Batch size should be 1"
+            self._encode_features(input_features)
+        n = int(ids.shape[1])
+        K1, V = self.config.medusa_num_heads + 1, self.config.vocab_size
+        out = torch.empty(K1, 1, n, V, dtype=torch.float32)
+        lib = _lib.load()
+        _check(lib, self._handle,
+               lib.wm_forward(self._handle, C.cast(ids.data_ptr(), C.POINTER(C.c_int32)), n,
+                              C.cast(out.data_ptr(), C.POINTER(C.c_float))), "wm_forward")
+
+        class _Out:
+            pass
+
+        o = _Out()
+        o.logits = (out[:1] if disable_medusa else out).to(self._device)
+        o.loss = None
+        return o
+
+    __call__ = forward
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        if self._state_dict is None:
+            raise RuntimeError("state dict was released")
+        return dict(self._state_dict)
+
+    def parameters(self):
+        return iter(self.state_dict().values())
 
     # ------------------------------------------------------------------ parity taps
     def last_logits(self, which: int) -> torch.Tensor:
