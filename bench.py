@@ -235,6 +235,8 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=6, help="speculative iterations per step of the CPU arm / baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other regimes and the K sweep")
+    ap.add_argument("--streams", type=int, default=4,
+                    help="concurrent streams per GPU of the multi-stream measurement (detail.multi_stream; BASELINE configs[3])")
     ap.add_argument("--dump-tokens", default=None, help="write this rank's token lists (JSON) to PATH.rank<r>")
     args = ap.parse_args()
 
@@ -372,6 +374,38 @@ def main():
                 sK = summarize(cK, trK, peak)
                 k_sweep[str(K)] = {k: sK[k] for k in ("tokens_per_s", "ms_per_iteration", "tokens_per_iteration", "mean_accept", "frac")}
                 mK.close()
+    # ---- BASELINE configs[3]: concurrent streams per GPU.  S engines share the weight blob and
+    # decode on n_sm / S CTAs each; 2 S clips per GPU (two waves).  Rank 0 measures; every stream's tokens are checked
+    # against the batch-1 run of the same clip.
+    multi = None
+    if rank == 0 and not args.no_extras and args.streams > 1:
+        from whisper_medusa_b200 import StreamGroup
+
+        try:
+            n_clips = 2 * args.streams
+            mclips = [clips[i % len(clips)] for i in range(n_clips)]
+            want = [outs[i % len(clips)] if (i % len(clips)) < args.steps else None for i in range(n_clips)]
+            grp = StreamGroup(cfg, None, device, n_streams=args.streams, weights_from=model)
+            gkw = dict(language=language, exponential_decay_length_penalty=PENALTY, posterior_alpha=alpha)
+            grp.generate_from_pcm(mclips[: args.streams], **dict(gkw, max_iters=4))
+            torch.cuda.synchronize(device)
+            got = [o[0].tolist() for o in grp.generate_from_pcm(mclips, **gkw)]
+            bad = [i for i, (g_, w_) in enumerate(zip(got, want)) if w_ is not None and g_ != w_]
+            if bad:
+                raise SystemExit(f"bench: concurrent streams {bad} differ from their batch-1 runs")
+            sM = summarize(cfg, grp.last_traces, peak)
+            enc_s = sum(t.ms_encoder + t.ms_mel for t in grp.last_traces) / 1e3
+            dec_s = max(1e-9, grp.last_wall_s - enc_s)      # the encoders are full-GPU GEMM kernels: they serialise
+            multi = {"streams": args.streams, "ctas_per_stream": grp.ctas_per_stream, "clips": n_clips,
+                     "tokens_per_s_e2e": sM["tokens"] / grp.last_wall_s, "tokens_per_s_decode_phase": sM["tokens"] / dec_s,
+                     "ms_per_iteration_per_stream": sM["ms_per_iteration"], "achieved_gbs": sM["bytes_eng"] / dec_s / 1e9,
+                     "frac": sM["bytes_eng"] / dec_s / 1e9 / peak, "vs_batch1_decode": (sM["tokens"] / dec_s) / sm["tokens_per_s"],
+                     "validated": "every stream == its batch-1 tokens", "wall_s": grp.last_wall_s, "encoder_s": enc_s}
+            grp.close()
+        except SystemExit:
+            raise
+        except Exception as e:  # noqa: BLE001
+            multi = {"streams": args.streams, "error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -407,7 +441,7 @@ def main():
                    "two_sweep_iterations": sm["two_sweep_iterations"],
                    "ms_mel": float(allv[0, 5]) / args.steps, "ms_encoder": float(allv[0, 4]) / args.steps,
                    "ms_decode": float(allv[0, 2]) / args.steps, "validated": validated,
-                   "regimes": regimes, "k_sweep": k_sweep},
+                   "regimes": regimes, "k_sweep": k_sweep, "multi_stream": multi},
     }
     if not args.no_cpu_baseline:
         try:

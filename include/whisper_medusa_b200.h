@@ -129,7 +129,11 @@ int64_t wm_last_launches(wm_handle* h, int32_t what);
  * ring (grid barriers only); 0 = CUDA graphs of stage kernels (debug / per-stage profiling, and the automatic
  * default for a decoder width the ring kernel is not instantiated for).  Returns the previous mode. */
 int wm_set_decode_mode(wm_handle* h, int32_t mode);
-/* Engine options: "decode_mode" (as above); "enc_gemm" 1 = tcgen05/TMA/TMEM encoder GEMM (default),
+/* Device address of the packed weights once loaded: a second handle on the same GPU adopts it (wm_adopt_weights)
+ * instead of holding its own copy -- how S concurrent streams share one blob. */
+void* wm_weights_device_ptr(wm_handle* h);
+/* Engine options: "decode_ctas" = CTAs of the decode grid (default: every SM; S handles with n_sm / S each decode S
+ * streams concurrently -- SURVEY 8(f) rank 3, the reference is batch 1 at model.py:1451); "decode_mode" (as above); "enc_gemm" 1 = tcgen05/TMA/TMEM encoder GEMM (default),
  * 0 = mma.sync encoder GEMM (cross-check); "profile" 1 = record the stage timeline below. */
 int wm_set_option(wm_handle* h, const char* key, int32_t value);
 /* Debug: per-stage timeline of the last persistent iteration (after wm_set_option(h, "profile", 1)).

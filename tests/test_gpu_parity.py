@@ -389,3 +389,40 @@ def test_checkpoint_directory_and_eval_driver_on_gpu(tmp_path):
     wer, cer, table = E.evaluate_rows(rows, transcribe, default_language="en")
     assert len(table["prediction"]) == 3 and all(p for p in table["prediction"]) and wer > 0
     m2.close()
+
+
+@pytest.mark.parametrize("ctas", [8, 37])
+@pytest.mark.parametrize("name", ["micro_linear_k4", "micro_block_k10", "tiny_linear_k4", "tiny_block_k4"])
+def test_partial_grids_give_the_same_tokens(name, ctas):
+    """option "decode_ctas": the persistent kernel on a fraction of the SMs (every CTA then owns several attention items /
+    more weight rows per stage) must produce the tokens of the full grid."""
+    from whisper_medusa_b200 import WhisperMedusaModel
+
+    g, cfg, seed, stream, kw = _load(name)
+    m = WhisperMedusaModel(cfg, synthetic_state_dict(cfg, seed=seed)).to("cuda:0")
+    m.set_option("decode_ctas", ctas)
+    out = m.generate_from_pcm(synthetic_audio(float(g["audio_seconds"]), stream_id=stream), **kw)[0].tolist()
+    assert out == g["tokens"].tolist() and m.last_trace.accept_lengths == g["accept_lengths"].tolist()
+    assert m.last_trace.launches_decode == m.last_trace.iterations
+    m.close()
+
+
+def test_stream_group_equals_single_stream_runs():
+    """SURVEY 8(f) rank 3 (the reference is batch 1, model.py:1451): S engines share one weight blob, each decodes on
+    n_sm / S CTAs, S streams concurrently; every stream's tokens are those of its batch-1 run.  Also the batched
+    generate(input_features[B, 80, 3000])."""
+    from whisper_medusa_b200 import StreamGroup
+
+    g, cfg, seed, stream, kw = _load("tiny_linear_k4")
+    sd = synthetic_state_dict(cfg, seed=seed)
+    single, _ = _model("tiny_linear_k4")
+    clips = [synthetic_audio(5.0, stream_id=40 + i) for i in range(6)]
+    want = [single.generate_from_pcm(c, **kw)[0].tolist() for c in clips]
+    for S in (2, 4):
+        grp = StreamGroup(cfg, sd, "cuda:0", n_streams=S)
+        got = [o[0].tolist() for o in grp.generate_from_pcm(clips, **kw)]
+        assert got == want, S
+        feats = torch.stack([torch.from_numpy(W.log_mel_spectrogram(c)) for c in clips[:3]])
+        assert [o[0].tolist() for o in grp.generate(feats, **kw)] == want[:3]
+        assert all(t.launches_decode == t.iterations for t in grp.last_traces)
+        grp.close()

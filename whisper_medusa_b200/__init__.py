@@ -5,5 +5,6 @@
 """
 from .config import MedusaConfig, MedusaGenerationConfig  # noqa: F401
 from .model import EngineError, WhisperMedusaModel  # noqa: F401
+from .streams import StreamGroup  # noqa: F401
 
-__all__ = ["WhisperMedusaModel", "MedusaConfig", "MedusaGenerationConfig", "EngineError"]
+__all__ = ["WhisperMedusaModel", "StreamGroup", "MedusaConfig", "MedusaGenerationConfig", "EngineError"]

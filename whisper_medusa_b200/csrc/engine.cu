@@ -37,6 +37,7 @@ struct wm_handle {
   wm_config cfg;
   int device = 0;
   int n_sm = 0;
+  int n_cta = 0;           // CTAs of the decode kernels (default: every SM; option "decode_ctas" partitions the GPU between streams)
   cudaStream_t stream = nullptr;
   std::string err;
   // weights
@@ -203,6 +204,25 @@ static cudaError_t dalloc(T** p, size_t elems) {
   return cudaMemset(*p, 0, elems * sizeof(T));
 }
 
+// How the decode stages split over the n_cta CTAs of the decode grid: key chunks per head of the cross-attention
+// stage (a chunk must fit one ring slot: <= WM_CH_MAX keys) and vocabulary segments per row of the logits scan.
+static void set_decode_split(wm_handle* h) {
+  DecModel& m = h->hm;
+  const int min_chunks = (h->S + WM_CH_MAX_KEYS - 1) / WM_CH_MAX_KEYS;
+  m.cross_chunks = h->n_cta / h->cfg.n_heads;
+  if (m.cross_chunks < min_chunks) m.cross_chunks = min_chunks;
+  if (m.cross_chunks > WM_CROSS_CHUNKS) m.cross_chunks = WM_CROSS_CHUNKS;
+  m.sel_nseg = h->n_cta / (h->cfg.medusa_num_heads + 1);
+  if (m.sel_nseg < 1) m.sel_nseg = 1;
+  if (m.sel_nseg > 32) m.sel_nseg = 32;
+}
+// graph / persistent_simple stages hold at most 3 16-row units per warp (stage_gemm): the vocabulary projection
+// needs enough CTAs for that; the ring kernel has no such limit
+static bool simple_modes_fit(const wm_handle* h) {
+  const int rows = (h->cfg.vocab_size + h->n_cta - 1) / h->n_cta;
+  return (rows + 15) / 16 <= 3 * (WM_DEC_THREADS / 32);
+}
+
 extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   if (!cfg || !out) return WM_ERR_INVALID;
   *out = nullptr;
@@ -229,6 +249,7 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(h, WM_ERR_UNSUPPORTED, "this engine is built for sm_100a (B200) only");
   h->n_sm = prop.multiProcessorCount;
+  h->n_cta = h->n_sm;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
 
@@ -274,16 +295,11 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   CK(dalloc(&m.carry, d));
   CK(dalloc(&m.cross_part, (size_t)c.n_heads * WM_CROSS_CHUNKS * WM_MAX_T * (WM_HEAD_DIM + 2)));
   CK(dalloc(&m.cross_cnt, (size_t)c.n_heads));
-  m.cross_chunks = h->n_sm / c.n_heads;
-  if (m.cross_chunks < 1) m.cross_chunks = 1;
-  if (m.cross_chunks > WM_CROSS_CHUNKS) m.cross_chunks = WM_CROSS_CHUNKS;
+  set_decode_split(h);
   if (f % d != 0 || f / d > 8 || h->n_sm < (int)(f / d)) return fail(h, WM_ERR_UNSUPPORTED, "ffn_dim must be a multiple (<= 8x) of d_model");
   CK(dalloc(&m.gemm_part, (size_t)8 * WM_MAX_T * d));
   CK(dalloc(&m.gemm_cnt, (size_t)h->n_sm));
   CK(dalloc(&m.sel_part, (size_t)WM_MAX_T * 32 * 4));
-  m.sel_nseg = h->n_sm / (c.medusa_num_heads + 1);
-  if (m.sel_nseg < 1) m.sel_nseg = 1;
-  if (m.sel_nseg > 32) m.sel_nseg = 32;
   CK(dalloc(&m.logits_a, (size_t)WM_MAX_T * V));
   CK(dalloc(&m.logits_b, (size_t)WM_MAX_T * V));
   CK(dalloc(&h->st, 1));
@@ -297,7 +313,7 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   CK(cudaMallocHost((void**)&h->h_init, sizeof(DecState)));
   CK(cudaMallocHost((void**)&h->h_pen, (size_t)(WM_MAX_POS + 32) * sizeof(float)));
 
-  h->hi.n_sm = h->n_sm; h->hi.H = c.n_heads; h->hi.K = c.medusa_num_heads; h->hi.n_layers = c.dec_layers;
+  h->hi.n_sm = h->n_cta; h->hi.H = c.n_heads; h->hi.K = c.medusa_num_heads; h->hi.n_layers = c.dec_layers;
   h->hi.has_block = m.has_block;
   h->hi.d = (int)d;
   h->hi.smem = dec_smem_bytes((int)d, (int)f);
@@ -317,11 +333,7 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   h->tc_ok = (enc_gemm_tc_configure() == cudaSuccess);
   h->enc_gemm_impl = h->tc_ok ? 1 : 0;   // tcgen05/TMA GEMM by default; option "enc_gemm" = 0 selects the mma.sync kernel
   (void)cudaGetLastError();
-  // the skinny-GEMM work split assumes at most WM_MAXR(3) 16-row units per warp
-  {
-    const int rows = (int)((V + h->n_sm - 1) / h->n_sm);
-    if ((rows + 15) / 16 > 3 * (WM_DEC_THREADS / 32)) return fail(h, WM_ERR_UNSUPPORTED, "too few SMs for the vocab projection split");
-  }
+  if (!simple_modes_fit(h) && !h->hi.smem_ring) return fail(h, WM_ERR_UNSUPPORTED, "too few SMs for the vocab projection split");
   return WM_OK;
 }
 
@@ -410,7 +422,7 @@ static int bind_weights(wm_handle* h) {
     // weight-chunk schedule of the ring producer (depends on the weight addresses)
     std::vector<ChunkDesc> tab;
     std::vector<int> off;
-    dec_build_chunk_table(m, h->n_sm, tab, off);
+    dec_build_chunk_table(m, h->n_cta, tab, off);
     if (h->chunk_tab) { cudaFree(h->chunk_tab); h->chunk_tab = nullptr; }
     if (h->chunk_off) { cudaFree(h->chunk_off); h->chunk_off = nullptr; }
     CK(cudaMalloc((void**)&h->chunk_tab, tab.size() * sizeof(ChunkDesc)));
@@ -420,7 +432,7 @@ static int bind_weights(wm_handle* h) {
     m.chunk_tab = h->chunk_tab;
     m.chunk_off = h->chunk_off;
     std::vector<CtaStage> stab;
-    dec_build_stage_table(m, h->n_sm, stab);
+    dec_build_stage_table(m, h->n_cta, stab);
     if (h->stage_tab) { cudaFree(h->stage_tab); h->stage_tab = nullptr; }
     CK(cudaMalloc((void**)&h->stage_tab, stab.size() * sizeof(CtaStage)));
     CK(cudaMemcpy(h->stage_tab, stab.data(), stab.size() * sizeof(CtaStage), cudaMemcpyHostToDevice));
@@ -797,7 +809,31 @@ extern "C" int wm_set_option(wm_handle* h, const char* key, int32_t value) {
   const std::string k(key);
   if (k == "decode_mode") {
     if (value < 0 || value > 2) return fail(h, WM_ERR_INVALID, "decode_mode must be 0, 1 or 2");
+    if (value < 2 && !simple_modes_fit(h)) return fail(h, WM_ERR_UNSUPPORTED, "decode modes 0 / 1 need more CTAs for the vocabulary projection");
+    if (value == 2 && !h->hi.smem_ring) return fail(h, WM_ERR_UNSUPPORTED, "the ring kernel is not instantiated for this decoder width");
     h->decode_mode = value;
+    return WM_OK;
+  }
+  if (k == "decode_ctas") {
+    // Size of the decode grid.  Default = every SM (lowest latency for one stream).  Several handles that share one
+    // weight blob and use 1/S of the SMs each run S streams CONCURRENTLY (their cooperative kernels are co-resident):
+    // a stage chain is latency-bound, so S partitions move S times the bytes in about the same time.
+    if (value < (int)(h->cfg.ffn_dim / h->cfg.d_model) || value > h->n_sm) return fail(h, WM_ERR_INVALID, "decode_ctas out of range");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_cta = value;
+    h->hi.n_sm = value;
+    set_decode_split(h);
+    for (auto& kv : h->graph_a) cudaGraphExecDestroy(kv.second);
+    h->graph_a.clear();
+    if (h->graph_b) { cudaGraphExecDestroy(h->graph_b); h->graph_b = nullptr; }
+    if (h->graph_tail) { cudaGraphExecDestroy(h->graph_tail); h->graph_tail = nullptr; }
+    if (!simple_modes_fit(h)) {
+      if (!h->hi.smem_ring) return fail(h, WM_ERR_UNSUPPORTED, "too few CTAs for this model without the ring kernel");
+      h->decode_mode = 2;
+    }
+    if (h->wready) return bind_weights(h);   // the per-CTA stage / chunk tables depend on the grid
+    CK(cudaMemcpy(h->dm, &h->hm, sizeof(DecModel), cudaMemcpyHostToDevice));
     return WM_OK;
   }
   if (k == "profile") {
@@ -849,6 +885,9 @@ extern "C" int wm_get_stage_profile(wm_handle* h, int64_t* out, int32_t cap_rows
 extern "C" int wm_set_decode_mode(wm_handle* h, int32_t mode) {
   if (!h) return WM_ERR_INVALID;
   int prev = h->decode_mode;
-  if (mode >= 0 && mode <= 2) h->decode_mode = mode;
+  if (mode >= 0 && mode <= 2 && wm_set_option(h, "decode_mode", mode) != WM_OK) return WM_ERR_UNSUPPORTED;
   return prev;
 }
+// Device address of the packed weights (so that further handles on the same GPU can wm_adopt_weights them: one copy
+// of the 3.1 GB blob serves every concurrent stream).
+extern "C" void* wm_weights_device_ptr(wm_handle* h) { return (h && h->wready) ? (void*)h->wdev : nullptr; }

@@ -147,8 +147,12 @@ class WhisperMedusaModel:
             max_source_positions=c.max_source_positions, max_target_positions=c.max_target_positions,
             medusa_num_heads=c.medusa_num_heads, medusa_block=1 if c.is_block else 0)
 
-    def to(self, device: Union[str, torch.device], broadcast_src: Optional[int] = None) -> "WhisperMedusaModel":
+    def to(self, device: Union[str, torch.device], broadcast_src: Optional[int] = None,
+           weights_from: Optional["WhisperMedusaModel"] = None) -> "WhisperMedusaModel":
         """Create the engine on ``device`` and upload the packed weights.
+
+        ``weights_from`` = another model of the same shape already on this GPU: its device blob is adopted instead
+        of a second upload (every concurrent stream of a ``StreamGroup`` reads the same 3.1 GB).
 
         With ``broadcast_src`` (inside an initialised ``torch.distributed`` NCCL group) only that rank
         packs the checkpoint; the blob reaches the other GPUs with one NCCL broadcast over NVLink and
@@ -174,7 +178,16 @@ class WhisperMedusaModel:
         self._handle = handle
         self._device = torch.device("cuda", index)
         nbytes = lib.wm_weights_nbytes(handle)
-        if broadcast_src is None:
+        if weights_from is not None:
+            weights_from._require_engine()
+            if weights_from._device != self._device or lib.wm_weights_nbytes(weights_from._handle) != nbytes:
+                raise EngineError("weights_from must be a model of the same shape on the same device")
+            ptr = lib.wm_weights_device_ptr(weights_from._handle)
+            if not ptr:
+                raise EngineError("weights_from has no weights loaded")
+            self._weights_owner = weights_from     # keep the owning engine alive
+            _check(lib, handle, lib.wm_adopt_weights(handle, C.c_void_p(ptr), nbytes), "wm_adopt_weights")
+        elif broadcast_src is None:
             if self._state_dict is None:
                 raise RuntimeError("no state dict to upload")
             blob = pack_blob(handle, self.config, self._state_dict)
