@@ -45,6 +45,8 @@ def main():
     model = WhisperMedusaModel(cfg, synthetic_state_dict(cfg, seed=arg("--seed", 0))).to("cuda:0")
     gen_kw = {"medusa_temperature": 0.0} if "--temp0" in sys.argv else {}
     model.set_decode_mode("persistent")
+    if "--ctas" in sys.argv:      # decode grid smaller than the GPU (one partition of a StreamGroup)
+        model.set_option("decode_ctas", arg("--ctas", 37))
     if "--tc" in sys.argv:
         model.set_option("enc_gemm", 1)
     if "--no-prof" in sys.argv:     # plain run (e.g. under ncu): no timeline
