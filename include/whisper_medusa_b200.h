@@ -66,6 +66,9 @@ typedef struct wm_gen_params {
   int32_t penalty_start;       /* ExponentialDecayLengthPenalty start_index, <0 = off */
   float penalty_factor;
   int32_t max_iters;           /* 0 = run to completion; >0 = stop after this many iterations */
+  int32_t tree_attention;      /* branching medusa_choices only: 0 = reference behaviour (verify rows attend causally over
+                                * cache order; medusa_attn_mask is built but never applied, model.py / medusa_utils.py:329-358),
+                                * 1 = every tree node attends to its ancestors only (true tree attention) */
 } wm_gen_params;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
@@ -85,6 +88,10 @@ size_t wm_weights_nbytes(wm_handle* h);
 int wm_load_weights(wm_handle* h, const void* host_blob, size_t nbytes);
 /* Use a caller-owned DEVICE blob (e.g. one filled by an NCCL broadcast); not freed by the handle. */
 int wm_adopt_weights(wm_handle* h, void* device_blob, size_t nbytes);
+
+/* ---- candidate tree (medusa_utils.py:305-421 generate_medusa_buffers, :446-457 per-head top-k) ------------- */
+/* choices[0..K]: choices[0] = 1; all ones = top-1 chain (default).  Branching trees: at most 16 nodes, 32 paths, k <= 4. */
+int wm_set_medusa_choices(wm_handle* h, const int32_t* choices, int32_t n);
 
 /* ---- logits processors (model.py:1168-1207; HF logits_process.py:1893-1901,1847-1862) -- */
 int wm_set_suppress(wm_handle* h, const int32_t* suppress_ids, int32_t n_suppress,

@@ -41,12 +41,23 @@ GROUPS = {
     "micro_blk_pen": ("micro", 10, "medusa_block", 10, 700, 140, (20, 1.05), 1.0, 0.3, 0.09),
     "tiny_lin_t1": ("tiny.en", 4, "base_head", 4, 800, 120, None, 1.0, 0.3, 0.09),
     "tiny_blk_pen": ("tiny.en", 4, "medusa_block", 4, 900, 120, (30, 1.03), 1.0, 0.3, 0.09),
+    # branching medusa_choices (TREE_CHOICES below): per-head top-k, tree verify in the reference's own way (its
+    # medusa_attn_mask is never applied), gathered KV rows, best-path selection by likelihood
+    "micro_tree122_t1": ("micro", 2, "base_head", 8, 1000, 100, None, 1.0, 0.3, 0.09),
+    "micro_tree122_t0": ("micro", 2, "base_head", 8, 1100, 100, None, 0.0, 0.3, 0.09),
+    "micro_tree1321_t1": ("micro", 3, "base_head", 8, 1200, 100, (20, 1.05), 1.0, 0.3, 0.09),
+    "micro_tree12121_t0": ("micro", 4, "base_head", 6, 1300, 100, None, 0.0, 0.3, 0.09),
+    "micro_blk_tree122_t1": ("micro", 2, "medusa_block", 8, 1400, 100, None, 1.0, 0.3, 0.09),
 }
+TREE_CHOICES = {"micro_tree122_t1": [1, 2, 2], "micro_tree122_t0": [1, 2, 2], "micro_tree1321_t1": [1, 3, 2, 1],
+                "micro_tree12121_t0": [1, 2, 1, 2, 1], "micro_blk_tree122_t1": [1, 2, 2]}
 
 
 def stream_inputs(group: str, s: int):
     preset, heads, htype, n, base, max_len, pen, temp, alpha, thr = GROUPS[group]
     cfg = preset_config(preset, heads=heads, heads_type=htype)
+    if group in TREE_CHOICES:
+        cfg.medusa_choices = list(TREE_CHOICES[group])
     sd = synthetic_state_dict(cfg, seed=base + s)
     pcm = synthetic_audio(5.0, stream_id=base + s)
     return cfg, sd, pcm, max_len, pen, temp, alpha, thr

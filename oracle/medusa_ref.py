@@ -14,9 +14,12 @@ Restatement of the reference's Medusa speculative decode loop and its helpers, f
 * logits processors: HF ``generation/logits_process.py:1893-1901`` (suppress),
   ``:1847-1862`` (begin-suppress), ``:1742-1772`` (EOS exponential decay).
 
-"Parity unpinned" caveat: the reference's ``WhisperMedusaModel`` cannot be imported in this
-environment, so the loop below is pinned only by the invariants in
-SURVEY.md 3.3 (asserted inline) and by the helper functions above.
+Pinning: the reference's package cannot be imported under the installed transformers, but
+``oracle/ref_harness.py`` executes the VERBATIM source of its loop (``_medusa_greedy_search``, ``forward``,
+``_forward_medusa_block``, ``_update_medusa_outputs``, all of ``medusa_utils.py``) on the installed Whisper modules;
+``tests/test_ref_loop_pin.py`` holds this restatement to those outputs bit-for-bit on 120 unselected streams (chains and
+branching trees, Linear and Block heads, both acceptance rules, length penalty / EOS), frozen in
+``tests/golden/ref_loop_streams.npz``.
 """
 from __future__ import annotations
 
@@ -174,9 +177,13 @@ class LoopTrace:
 
 def medusa_greedy_search(w: W.RefWeights, cfg, enc: torch.Tensor, prompt: Sequence[int], gp: GenParams,
                          regime: str = "fp32", capture_logits: int = 0,
-                         max_iters: Optional[int] = None) -> LoopTrace:
+                         max_iters: Optional[int] = None, tree_attention: bool = False) -> LoopTrace:
     """Batch-1 restatement of reference ``model.py:404-835``; returns the full ``input_ids``
-    (prompt included) after the post-EOS fill (``:798-810``)."""
+    (prompt included) after the post-EOS fill (``:798-810``).
+
+    ``tree_attention=True`` is NOT reference behaviour (the reference builds ``medusa_attn_mask`` and never applies it,
+    SURVEY.md 3.3): every verify row then attends to the cache and to its own ancestors only -- the mode the engine offers
+    as ``generate(tree_attention=True)`` for branching ``medusa_choices``."""
     H = cfg.medusa_num_heads
     choices = list(gp.medusa_choices) if gp.medusa_choices else list(cfg.medusa_choices)
     bufs = generate_medusa_buffers(choices)                      # model.py:615-630
@@ -186,6 +193,14 @@ def medusa_greedy_search(w: W.RefWeights, cfg, enc: torch.Tensor, prompt: Sequen
     cache = W.new_cache(cfg)
     tr = LoopTrace(sequences=input_ids)
     unfinished = True
+    allowed = None
+    if tree_attention:
+        n_tree = int(pos_tbl.shape[0])
+        allowed = torch.eye(n_tree, dtype=torch.bool)
+        for c in range(retrieve.shape[0]):
+            path = retrieve[c].tolist()
+            for j, node in enumerate(path):
+                allowed[node, path[: j + 1]] = True
     while True:
         L = len(input_ids)
         kv = cache.length
@@ -201,7 +216,7 @@ def medusa_greedy_search(w: W.RefWeights, cfg, enc: torch.Tensor, prompt: Sequen
         # B: verify pass on a *copy* of the cache (tree_outputs.past_key_values, model.py:383-401)
         vcache = cache.clone()
         pos_b = (pos_tbl + L).tolist()
-        hidden_b = W.decoder_forward(w, cfg, tree_candidates.tolist(), pos_b, enc, vcache, regime)
+        hidden_b = W.decoder_forward(w, cfg, tree_candidates.tolist(), pos_b, enc, vcache, regime, allowed)
         logits_b_raw = W.medusa_logits(w, cfg, hidden_b, enc, vcache, True, regime)[0]    # [n_tree, V]
         logits_b = process_logits(logits_b_raw, L, gp)                                    # B1
         vlog = logits_b[retrieve]                                                         # [n_cand, H+1, V]

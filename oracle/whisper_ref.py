@@ -247,7 +247,8 @@ class RefCache:
 
 
 def _decoder_layer(w: RefWeights, cfg, lp: str, li: int, x: torch.Tensor, enc: torch.Tensor,
-                   cache: RefCache, regime: str, causal_offset: Optional[int]) -> torch.Tensor:
+                   cache: RefCache, regime: str, causal_offset: Optional[int],
+                   new_allowed: Optional[torch.Tensor] = None) -> torch.Tensor:
     """HF ``modeling_whisper.py:449-506`` (``WhisperDecoderLayer.forward``).
 
     ``causal_offset`` = number of cached positions before this call (query t sees cached
@@ -274,6 +275,9 @@ def _decoder_layer(w: RefWeights, cfg, lp: str, li: int, x: torch.Tensor, enc: t
     if causal_offset is not None:
         past = n - T
         mask = torch.arange(n)[None, :] > (past + torch.arange(T))[:, None]
+        if new_allowed is not None:   # true tree attention (NOT what the reference does): new row t sees new row j only if allowed
+            mask = mask.clone()
+            mask[:, past:] |= ~new_allowed
         scores = scores.masked_fill(mask[None], float("-inf"))
     o = _merge_heads(torch.softmax(scores, dim=-1) @ _split_heads(V, H))
     x = x + w.lin(o, f"{lp}.self_attn.out_proj")
@@ -294,7 +298,7 @@ def _decoder_layer(w: RefWeights, cfg, lp: str, li: int, x: torch.Tensor, enc: t
 
 
 def decoder_forward(w: RefWeights, cfg, ids: List[int], positions: List[int], enc: torch.Tensor,
-                    cache: RefCache, regime: str = "fp32") -> torch.Tensor:
+                    cache: RefCache, regime: str = "fp32", new_allowed: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Hidden states ``[T, d]`` for ``ids`` at explicit ``positions``; appends to ``cache``.
 
     Follows HF ``modeling_whisper.py:691-796`` (``WhisperDecoder.forward``): token + learned
@@ -308,7 +312,7 @@ def decoder_forward(w: RefWeights, cfg, ids: List[int], positions: List[int], en
     x = w[f"{p}.embed_tokens.weight"][idt] + w[f"{p}.embed_positions.weight"][pos]
     past = cache.length
     for i in range(cfg.decoder_layers):
-        x = _decoder_layer(w, cfg, f"{p}.layers.{i}", i, x, enc, cache, regime, past)
+        x = _decoder_layer(w, cfg, f"{p}.layers.{i}", i, x, enc, cache, regime, past, new_allowed)
     return w.ln(x, f"{p}.layer_norm")
 
 

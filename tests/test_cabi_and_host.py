@@ -117,8 +117,11 @@ def test_config_roundtrip_and_reference_errors(tmp_path):
         MedusaConfig(medusa_heads_type="nope", whisper_model_name="synthetic/whisper-micro")   # model.py:224-228
     with pytest.raises(OSError):
         WhisperMedusaModel.from_pretrained(str(tmp_path / "missing"))
-    with pytest.raises(NotImplementedError):
-        WhisperMedusaModel(MedusaConfig(medusa_num_heads=2, medusa_hidden_size=128, medusa_choices=[1, 2, 2],
+    # branching choices construct (the tree is checked against the engine's limits when the engine is created)
+    WhisperMedusaModel(MedusaConfig(medusa_num_heads=2, medusa_hidden_size=128, medusa_choices=[1, 2, 2],
+                                    whisper_model_name="synthetic/whisper-micro"), None)
+    with pytest.raises(ValueError):
+        WhisperMedusaModel(MedusaConfig(medusa_num_heads=2, medusa_hidden_size=128, medusa_choices=[1, 2],
                                         whisper_model_name="synthetic/whisper-micro"), None)
 
 

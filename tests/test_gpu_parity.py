@@ -426,3 +426,57 @@ def test_stream_group_equals_single_stream_runs():
         assert [o[0].tolist() for o in grp.generate(feats, **kw)] == want[:3]
         assert all(t.launches_decode == t.iterations for t in grp.last_traces)
         grp.close()
+
+
+@pytest.mark.parametrize("htype,heads,choices", [("base_head", 2, [1, 2, 2]), ("base_head", 3, [1, 3, 2, 1]),
+                                                 ("medusa_block", 2, [1, 2, 2]), ("base_head", 4, [1, 2, 1, 2, 1])])
+def test_branching_trees_both_attention_modes(htype, heads, choices):
+    """SURVEY 8(f) rank 4.  Branching medusa_choices: per-head top-k candidates, the tree verified in one pass, best
+    path by accept length / likelihood, surviving K/V rows gathered.  (i) tree_attention=False reproduces what the
+    reference does (its medusa_attn_mask is never applied) -- against the oracle here and against the reference's own
+    loop in test_engine_vs_the_reference_loop_on_unselected_streams; (ii) tree_attention=True (every node attends to
+    its ancestors only; sweep elision as for the chain) against the oracle with the mask; (iii) the property that makes
+    it speculative decoding proper: with exact-match acceptance the tree output IS the base model's greedy output, i.e.
+    the same tokens as the top-1 chain at temperature 0."""
+    from whisper_medusa_b200 import WhisperMedusaModel
+
+    for seed in (2, 3):
+        cfg = preset_config("micro", heads=heads, heads_type=htype)
+        cfg.medusa_choices = list(choices)
+        sd = synthetic_state_dict(cfg, seed=seed)
+        pcm = synthetic_audio(5.0, stream_id=seed)
+        m = WhisperMedusaModel(cfg, sd).to("cuda:0")
+        w = W.RefWeights(sd)
+        mel = torch.from_numpy(W.log_mel_spectrogram(pcm))
+        enc = W.encoder_forward(w, cfg, mel, "engine")
+        prompt = M.init_tokens(cfg, None)
+        for temp in (1.0, 0.0):
+            gp = M.gen_params(cfg, prompt, None, 100, temperature=temp)
+            for tree_attn in (False, True):
+                for mode in ("persistent", "graph"):
+                    m.set_decode_mode(mode)
+                    m.generate_from_pcm(pcm, max_length=100, medusa_temperature=temp, tree_attention=tree_attn)
+                    tr = M.medusa_greedy_search(w, cfg, enc, prompt, gp, "engine", tree_attention=tree_attn)
+                    assert m.last_trace.accept_lengths == tr.accept_lengths, (seed, temp, tree_attn, mode)
+                    assert m.last_trace.sequences == tr.sequences, (seed, temp, tree_attn, mode)
+        m.set_decode_mode("persistent")
+        m.generate_from_pcm(pcm, max_length=100, medusa_temperature=0.0, tree_attention=True)
+        tree_greedy = m.last_trace.sequences
+        m.close()
+        if htype == "base_head":
+            cfg1 = preset_config("micro", heads=heads, heads_type=htype)          # top-1 chain, same weights
+            m1 = WhisperMedusaModel(cfg1, sd).to("cuda:0")
+            m1.generate_from_pcm(pcm, max_length=100, medusa_temperature=0.0)
+            chain_greedy = m1.last_trace.sequences
+            m1.close()
+            n = min(len(tree_greedy), len(chain_greedy))
+            assert tree_greedy[:n] == chain_greedy[:n], seed
+
+
+def test_tree_limits_are_reported():
+    from whisper_medusa_b200 import WhisperMedusaModel
+
+    cfg = preset_config("micro", heads=4)
+    cfg.medusa_choices = [1, 6, 5, 4, 3]            # the example of the reference's docstring: 511 nodes
+    with pytest.raises(NotImplementedError):
+        WhisperMedusaModel(cfg, synthetic_state_dict(cfg, seed=0)).to("cuda:0")

@@ -27,7 +27,7 @@ class WmGenParams(C.Structure):
         ("max_length", C.c_int32), ("eos_token_id", C.c_int32), ("pad_token_id", C.c_int32),
         ("begin_index", C.c_int32), ("temperature", C.c_float), ("posterior_threshold", C.c_float),
         ("posterior_alpha", C.c_float), ("penalty_start", C.c_int32), ("penalty_factor", C.c_float),
-        ("max_iters", C.c_int32),
+        ("max_iters", C.c_int32), ("tree_attention", C.c_int32),
     ]
 
 
@@ -44,6 +44,7 @@ SYMBOLS = {
     "wm_weights_nbytes": (C.c_size_t, [C.c_void_p]),
     "wm_load_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "wm_adopt_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "wm_set_medusa_choices": (C.c_int, [C.c_void_p, _P(C.c_int32), C.c_int32]),
     "wm_set_suppress": (C.c_int, [C.c_void_p, _P(C.c_int32), C.c_int32, _P(C.c_int32), C.c_int32]),
     "wm_encode_pcm": (C.c_int, [C.c_void_p, _P(C.c_float), C.c_int32]),
     "wm_encode_mel": (C.c_int, [C.c_void_p, _P(C.c_float)]),

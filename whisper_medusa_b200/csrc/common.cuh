@@ -15,6 +15,21 @@
 namespace wm {
 
 struct StageInstr;
+
+// Candidate tree of a branching `medusa_choices` (reference medusa_utils.py:305-421 generate_medusa_buffers; built by the
+// host in wm_set_medusa_choices).  Nodes are numbered level by level; node 0 = the base-head token.  The engine holds at
+// most WM_MAX_T nodes, WM_TREE_MAX_CAND root-to-leaf paths and WM_TREE_MAX_TOPK candidates per head.
+#define WM_TREE_MAX_CAND 32
+#define WM_TREE_MAX_TOPK 4
+struct DecTree {
+  int n_tree, n_cand;
+  int depth[16];        // medusa_position_ids: level of the node
+  int rank[16];         // which of its head's top-k tokens the node carries (tree_indices - first index of the level)
+  int parent[16];       // parent node, -1 for the root
+  int topk[16];         // k of level i (topk[0] = 1)
+  unsigned int anc[16]; // bit j set: node j is the node itself or one of its ancestors (true tree attention)
+  int retrieve[WM_TREE_MAX_CAND][16];   // retrieve_indices: path c -> node at depth j
+};
 // one ring chunk: `nrows` (<= 16) rows of `copy_bytes` each, row r read at src + r * row_bytes and written at
 // slot + r * (slot row stride).  Weight chunks: rows of W (copy_bytes = d fp16); cross-attention chunks:
 // nrows = 1, one contiguous block of K or V rows.
@@ -190,12 +205,15 @@ struct DecState {
   int accept_last;
   int need_a;       // 1 => the newest token is not cached yet: run sweep A before the tail
   float temperature, post_thr, post_alpha;
+  int tree_attn;    // tree mode: 1 = rows attend to their ancestors only (true tree attention), 0 = reference behaviour
+  int keep_n;       // tree mode: K/V rows of the verify pass that survive (kept at rows L .. L+keep_n-1) ...
+  int keep_src[WM_MAX_T];   // ... and the cache rows they come from (keep_src[j] >= L + j)
   int ids[WM_MAX_POS + 32];
-  int cand[WM_MAX_T];            // candidate chain of the current iteration (c0, head 1..K)
+  int cand[WM_MAX_T];            // tokens of the candidate tree nodes (chain: c0, head 1..K)
   int accept_hist[WM_MAX_POS];
   // per-row statistics written by the logits scan, consumed by the accept step
   int row_argmax[WM_MAX_T];
-  float row_pc[WM_MAX_T];        // softmax prob of the candidate following the row
+  float row_pc[WM_MAX_T];        // [n]: softmax prob of node n's token in the posterior of its parent row (chain: parent = n-1)
   float row_thr[WM_MAX_T];
 };
 
@@ -204,6 +222,10 @@ struct DecModel {
   int n_layers;      // decoder layers (without the medusa block)
   int has_block;     // 1 => layers[n_layers] is the medusa block
   int K;             // medusa heads
+  int n_tree;        // rows of the verify pass: K+1 for the chain, tree nodes for branching medusa_choices
+  int has_tree;      // 1 => branching choices: `tree` describes the candidate tree
+  const DecTree* tree;
+  float* topk_part;  // [WM_MAX_T rows][32 segments][WM_TREE_MAX_TOPK]{value, index}: per-segment top-k of the tail scan
   DecLayer layers[WM_MAX_DEC_LAYERS];
   const __half* embed;   // [V, d] (also proj_out)
   const float* pos;      // [max_target_positions, d]

@@ -45,7 +45,7 @@ __device__ __forceinline__ PassGeom pass_geom(const DecModel* m, int mode) {
     g.T = st->L - st->kv_len;
     g.base = st->kv_len;
   } else if (mode == MODE_B) {
-    g.T = m->K + 1;
+    g.T = m->n_tree;
     g.base = st->L;
   } else {
     g.T = 1;
@@ -64,7 +64,9 @@ __device__ __forceinline__ void stage_embed(const DecModel* m, int mode, int cta
   for (int t = cta; t < g.T; t += ncta) {
     int tok = (mode == MODE_A) ? ldcg_i(&st->ids[g.base + t]) : ldcg_i(&st->cand[t]);
     const __half* e = m->embed + (size_t)tok * d;
-    const float* p = m->pos + (size_t)(g.base + t) * d;
+    // verify rows of a candidate tree sit at position L + depth (medusa_position_ids, medusa_utils.py:494-496)
+    const int posn = (mode == MODE_B && m->has_tree) ? g.base + m->tree->depth[t] : g.base + t;
+    const float* p = m->pos + (size_t)posn * d;
     float* x = m->x + (size_t)t * d;
     for (int j = threadIdx.x; j < d; j += WM_DEC_THREADS) x[j] = __half2float(e[j]) + p[j];
   }
@@ -365,6 +367,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
   float* s_st = s_p + WM_SA_MAXR * WM_MAX_POS;                     // [R] sum
   float* s_acc = s_st + 2 * WM_SA_MAXR;                            // [WM_DEC_THREADS / 8 groups][64]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool tree_mask = (mode == MODE_B) && m->has_tree && m->st->tree_attn;   // (tree_attn is constant during a generate call)
   int R = (H * T + ncta - 1) / ncta;
   if (R > WM_SA_MAXR) R = WM_SA_MAXR;
   if (R < 1) R = 1;
@@ -386,7 +389,8 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
       uint4 a[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) a[c] = ldcg_u4(k0 + c);
-      const bool ok0 = j0 <= g.base + t0 + r0;     // causal
+      bool ok0 = j0 <= g.base + t0 + r0;           // causal (over cache order: what the reference does for trees too)
+      if (tree_mask && j0 >= g.base) ok0 = ok0 && ((m->tree->anc[t0 + r0] >> (j0 - g.base)) & 1u);   // ancestors only
       s_p[r0 * WM_MAX_POS + j0] = ok0 ? dot64_h(s_q + r0 * 64, a) * 0.125f : -INFINITY;
     }
     cta_sync();
@@ -834,6 +838,9 @@ __device__ float block_sum(float v, float* s_val) {
 __device__ __forceinline__ int select_nseg(const DecModel* m, int /*ncta*/) { return m->sel_nseg; }
 // sel_part layout: [row][seg][4] = {max, argmax (int bits), sumexp, entropy term}
 
+// strict "comes after" in the candidate order (value descending, index ascending)
+__device__ __forceinline__ bool ranks_after(float v, int i, float pv, int pi) { return v < pv || (v == pv && i > pi); }
+
 __device__ __noinline__ void stage_select1(const DecModel* m, int mode, int cta, int ncta, unsigned char* smem_raw) {
   const DecState* st = m->st;
   const int V = m->V, K = m->K;
@@ -848,7 +855,10 @@ __device__ __noinline__ void stage_select1(const DecModel* m, int mode, int cta,
   const int seglen = (V + nseg - 1) / nseg;
   const float temp = st->temperature;
   const float inv_t = temp > 0.f ? 1.0f / temp : 1.0f;
-  for (int item = cta; item < (K + 1) * nseg; item += ncta) {
+  const bool tree = m->has_tree != 0;
+  const int n_rows = (mode == MODE_A) ? K + 1 : m->n_tree;
+  const int n_stat = tree ? n_rows : K;   // verify rows whose posterior is needed (rows that have a child)
+  for (int item = cta; item < n_rows * nseg; item += ncta) {
     const int r = item / nseg, sg = item - r * nseg;
     const int j0 = sg * seglen, j1 = min(V, j0 + seglen);
     const float* row = logits + (size_t)r * V;
@@ -860,7 +870,7 @@ __device__ __noinline__ void stage_select1(const DecModel* m, int mode, int cta,
     }
     block_argmax(bv, bi, s_val, s_idx);
     float z = 0.f;
-    if (mode == MODE_B && r < K && temp > 0.f && bv > -INFINITY) {
+    if (mode == MODE_B && r < n_stat && temp > 0.f && bv > -INFINITY) {
       for (int j = j0 + threadIdx.x; j < j1; j += WM_DEC_THREADS)
         z += expf((processed_logit(row, j, m->tok_mask, begin_on, eos, pen) - bv) * inv_t);
       z = block_sum(z, s_val);
@@ -868,6 +878,24 @@ __device__ __noinline__ void stage_select1(const DecModel* m, int mode, int cta,
     if (threadIdx.x == 0) {
       float* o = m->sel_part + ((size_t)r * WM_SEL_MAXSEG + sg) * 4;
       o[0] = bv; o[1] = __int_as_float(bi); o[2] = z;
+    }
+    if (mode == MODE_A && tree) {
+      // per-head top-k candidates (medusa_utils.py:446-457): the segment's first k entries in (value desc, index asc)
+      // order, one block-wide selection round per rank (k <= WM_TREE_MAX_TOPK; tail only)
+      const int kk = m->tree->topk[r];
+      float* tp = m->topk_part + ((size_t)r * WM_SEL_MAXSEG + sg) * WM_TREE_MAX_TOPK * 2;
+      float pv = bv; int pi = bi;
+      if (threadIdx.x == 0) { tp[0] = pv; tp[1] = __int_as_float(pi); }
+      for (int q = 1; q < kk; ++q) {
+        float cv = -INFINITY; int ci = 0x7fffffff;
+        for (int j = j0 + threadIdx.x; j < j1; j += WM_DEC_THREADS) {
+          const float v = processed_logit(row, j, m->tok_mask, begin_on, eos, pen);
+          if (ranks_after(v, j, pv, pi) && (v > cv)) { cv = v; ci = j; }
+        }
+        block_argmax(cv, ci, s_val, s_idx);
+        pv = cv; pi = ci;
+        if (threadIdx.x == 0) { tp[2 * q] = pv; tp[2 * q + 1] = __int_as_float(pi); }
+      }
     }
   }
 }
@@ -910,7 +938,9 @@ __device__ __noinline__ void stage_select2(const DecModel* m, int cta, int ncta,
   const int eos = st->eos;
   const int nseg = select_nseg(m, ncta);
   const int seglen = (V + nseg - 1) / nseg;
-  for (int item = cta; item < K * nseg; item += ncta) {   // evaluate_posterior reads logits[:, :-1]
+  const bool tree = m->has_tree != 0;
+  const int n_stat = tree ? m->n_tree : K;                // chain: evaluate_posterior reads logits[:, :-1]
+  for (int item = cta; item < n_stat * nseg; item += ncta) {
     const int r = item / nseg, sg = item - r * nseg;
     const int j0 = sg * seglen, j1 = min(V, j0 + seglen);
     const float* row = m->logits_b + (size_t)r * V;
@@ -924,9 +954,14 @@ __device__ __noinline__ void stage_select2(const DecModel* m, int cta, int ncta,
     ent = block_sum(ent, s_val);
     if (threadIdx.x == 0) {
       m->sel_part[((size_t)r * WM_SEL_MAXSEG + sg) * 4 + 3] = ent;
-      const int c = ldcg_i(&st->cand[r + 1]);
-      if (c >= j0 && c < j1)
-        st->row_pc[r] = expf((processed_logit(row, c, m->tok_mask, begin_on, eos, pen) - M) * inv_t) / Z;
+      // probability, under this row's posterior, of the token of every child node (chain: the one node r + 1)
+      const int n_lo = tree ? 1 : r + 1, n_hi = tree ? m->n_tree : r + 2;
+      for (int n = n_lo; n < n_hi; ++n) {
+        if (tree && m->tree->parent[n] != r) continue;
+        const int c = ldcg_i(&st->cand[n]);
+        if (c >= j0 && c < j1)
+          st->row_pc[n] = expf((processed_logit(row, c, m->tok_mask, begin_on, eos, pen) - M) * inv_t) / Z;
+      }
     }
   }
 }
@@ -935,10 +970,43 @@ __device__ __noinline__ void stage_select2(const DecModel* m, int cta, int ncta,
 __device__ __noinline__ void stage_select_fin(const DecModel* m, int ncta) {
   DecState* st = m->st;
   const int nseg = select_nseg(m, ncta);
-  for (int r = threadIdx.x >> 5; r <= m->K; r += (WM_DEC_THREADS >> 5)) {   // warp per row
-    float M, Z, ent; int idx;
-    select_fold(m, r, nseg, 1.0f, M, idx, Z, ent);
-    if ((threadIdx.x & 31) == 0) st->cand[r] = idx;
+  if (!m->has_tree) {
+    for (int r = threadIdx.x >> 5; r <= m->K; r += (WM_DEC_THREADS >> 5)) {   // warp per row
+      float M, Z, ent; int idx;
+      select_fold(m, r, nseg, 1.0f, M, idx, Z, ent);
+      if ((threadIdx.x & 31) == 0) st->cand[r] = idx;
+    }
+    return;
+  }
+  // tree: merge the per-segment top-k lists of head row r (lane = segment; every list is sorted), k rounds; the q-th
+  // winner is the token of every node of level r with rank q (tree_candidates = candidates_flat[tree_indices])
+  const DecTree* tr = m->tree;
+  const int lane = threadIdx.x & 31;
+  for (int r = threadIdx.x >> 5; r <= m->K; r += (WM_DEC_THREADS >> 5)) {
+    const int kk = tr->topk[r];
+    const float* tp = m->topk_part + ((size_t)r * WM_SEL_MAXSEG + lane) * WM_TREE_MAX_TOPK * 2;
+    float lv[WM_TREE_MAX_TOPK]; int li[WM_TREE_MAX_TOPK];
+#pragma unroll
+    for (int q = 0; q < WM_TREE_MAX_TOPK; ++q) {
+      lv[q] = -INFINITY; li[q] = 0x7fffffff;
+      if (lane < nseg && q < kk) { lv[q] = __ldcg(tp + 2 * q); li[q] = __float_as_int(__ldcg(tp + 2 * q + 1)); }
+    }
+    int p = 0;
+    for (int q = 0; q < kk; ++q) {
+      float v = -INFINITY; int i = 0x7fffffff;
+#pragma unroll
+      for (int e = 0; e < WM_TREE_MAX_TOPK; ++e)
+        if (e == p) { v = lv[e]; i = li[e]; }
+      float bv = v; int bi = i;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (v == bv && i == bi) ++p;                    // (indices are unique: exactly one lane advances)
+      if (lane < tr->n_tree && tr->depth[lane] == r && tr->rank[lane] == q) st->cand[lane] = bi;
+    }
   }
 }
 
@@ -986,7 +1054,7 @@ __device__ __noinline__ void stage_accept(const DecModel* m, int ncta) {
     const int L = st->L;
     const float temp = st->temperature;
     const int cand_l = (lane <= K) ? ldcg_i(&st->cand[lane]) : 0;
-    const float pc_l = (lane < K && temp != 0.f) ? ldcg_f(&st->row_pc[lane]) : 0.f;
+    const float pc_l = (lane < K && temp != 0.f) ? ldcg_f(&st->row_pc[lane + 1]) : 0.f;   // p(cand[lane + 1] | row lane)
     const int cand_next = __shfl_down_sync(0xffffffffu, cand_l, 1);
     bool ok = false;
     if (lane < K) ok = (temp == 0.f) ? (cand_next == s_arg[lane]) : (pc_l > s_thr[lane]);
@@ -1002,6 +1070,7 @@ __device__ __noinline__ void stage_accept(const DecModel* m, int ncta) {
       st->L = newL;
       st->kv_len = (a == 0) ? newL - 1 : newL;
       st->need_a = (a == 0) ? 1 : 0;
+      st->keep_n = 0;                        // chain: the surviving K/V rows are already where they belong
       st->accept_last = a;
       const int it = st->n_iter;
       st->accept_hist[it] = a;
@@ -1021,12 +1090,146 @@ __device__ __noinline__ void stage_accept(const DecModel* m, int ncta) {
 }
 
 // -----------------------------------------------------------------------------------------
+// stage: accept for a candidate TREE (branching medusa_choices; CTA 0)
+//   evaluate_posterior over all root-to-leaf paths (medusa_utils.py:526-588): accept length of a path = number of
+//   leading edges whose child token passes (typical acceptance: p_parent(child) > threshold(parent); temperature 0:
+//   child == argmax(parent)); best = longest, ties broken by the summed log-likelihood (first index at temperature 0,
+//   torch.argmax).  update_inference_inputs (:630-652) + _update_medusa_outputs (model.py:383-401): the tokens of the
+//   accepted prefix are appended and the K/V rows of its first `accept` nodes (one node when nothing was accepted) are
+//   kept -- they are gathered to rows L .. by stage_kv_compact.
+//   Reference behaviour (tree_attn = 0): the verify rows attended to ALL earlier tree rows, so the newest token is
+//   re-run by sweep A every iteration (need_a = 1), exactly like the reference's pass A.  With true tree attention
+//   (tree_attn = 1) a node only saw its ancestors: its hidden state and K/V row are what a re-run would compute, and
+//   the sweep is elided as in the chain case.
+// -----------------------------------------------------------------------------------------
+__device__ __noinline__ void stage_accept_tree(const DecModel* m, int ncta) {
+  __shared__ int s_arg[WM_MAX_T];
+  __shared__ float s_thr[WM_MAX_T];
+  __shared__ int s_a, s_node;
+  DecState* st = m->st;
+  const DecTree* tr = m->tree;
+  const int K = m->K, nt = tr->n_tree;
+  const int nseg = select_nseg(m, ncta);
+  const int lane = threadIdx.x & 31;
+  const float temp = st->temperature;
+  for (int r = threadIdx.x >> 5; r < nt; r += (WM_DEC_THREADS >> 5)) {   // warp per tree row
+    float M, Z, ent; int idx;
+    select_fold(m, r, nseg, temp > 0.f ? 1.0f / temp : 1.0f, M, idx, Z, ent);
+    if (lane == 0) {
+      st->row_argmax[r] = idx;
+      s_arg[r] = idx;
+      const float thr = fminf(st->post_thr, expf(ent) * st->post_alpha);
+      st->row_thr[r] = thr;
+      s_thr[r] = thr;
+    }
+  }
+  cta_sync();
+  if (threadIdx.x < 32) {
+    const int L = st->L;
+    // lane = node: its token and its probability under the parent's posterior
+    const int tok_n = (lane < nt) ? ldcg_i(&st->cand[lane]) : 0;
+    const float pc_n = (lane >= 1 && lane < nt && temp != 0.f) ? ldcg_f(&st->row_pc[lane]) : 0.f;
+    // lane = candidate path: walk its edges (every lane runs the loop -- the shuffles need the full warp --; lanes
+    // beyond the last path walk path 0 and are discarded)
+    int len = 0;
+    float like = 0.f;
+    {
+      const int c = min(lane, tr->n_cand - 1);
+      bool open = true;
+      for (int j = 0; j < K; ++j) {
+        const int node = tr->retrieve[c][j], child = tr->retrieve[c][j + 1];
+        const int ctok = __shfl_sync(0xffffffffu, tok_n, child);
+        const float cp = __shfl_sync(0xffffffffu, pc_n, child);
+        const bool ok = (temp == 0.f) ? (ctok == s_arg[node]) : (cp > s_thr[node]);
+        open = open && ok;
+        if (open) { ++len; if (temp != 0.f) like += logf(cp); }
+      }
+      if (lane >= tr->n_cand) len = -1;
+    }
+    int a = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a = max(a, __shfl_xor_sync(0xffffffffu, a, o));
+    // best path: longest; at temperature 0 the first such path, else the most likely one (first on ties)
+    float score = (lane < tr->n_cand && len == a) ? ((temp == 0.f || a == 0) ? 0.f : like) : -INFINITY;
+    int best = lane;
+    float bs = score;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+      if (os > bs || (os == bs && ob < best)) { bs = os; best = ob; }
+    }
+    if (a == 0) best = 0;
+    int n_new = a + 1;
+    // lane = depth along the best path
+    const int node_l = (lane <= K) ? tr->retrieve[best][lane] : 0;
+    int id = __shfl_sync(0xffffffffu, tok_n, node_l);
+    if (a == 0) { n_new = 2; if (lane == 1) id = s_arg[tr->retrieve[best][0]]; }
+    if (lane < n_new) st->ids[L + lane] = id;
+    const bool eos = __ballot_sync(0xffffffffu, lane < n_new && id == st->eos) != 0u;
+    const int keep = (a == 0) ? 1 : a;
+    const bool elide = st->tree_attn != 0 && a >= 1;     // true tree attention: node `a` was computed behind exactly its prefix
+    const int keep_rows = elide ? a + 1 : keep;
+    if (lane < keep_rows) st->keep_src[lane] = L + node_l;
+    if (lane == 0) {
+      const int newL = L + n_new;
+      st->L = newL;
+      st->kv_len = elide ? newL : newL - 1;
+      st->need_a = elide ? 0 : 1;
+      st->keep_n = keep_rows;
+      st->accept_last = a;
+      const int it = st->n_iter;
+      st->accept_hist[it] = a;
+      st->n_iter = it + 1;
+      bool done = eos || newL >= st->max_length || newL + K >= st->max_length;
+      if (st->max_iters > 0 && it + 1 >= st->max_iters) done = true;
+      if (done) st->done = 1;
+      s_a = elide ? a : -1;
+      s_node = tr->retrieve[best][a];
+    }
+  }
+  cta_sync();
+  if (s_a >= 1) {
+    const float* src = m->hidden + (size_t)s_node * m->d;
+    for (int j = threadIdx.x; j < m->d; j += WM_DEC_THREADS) m->carry[j] = ldcg_f(src + j);
+  }
+}
+
+// stage: gather the surviving K/V rows of a tree verify pass to rows L .. L+keep-1 of every layer's cache (reference
+// model.py:383-401: tree_past[:, :, select_indices][..., :accept]).  One (layer, K|V) item per CTA turn; rows move in
+// path order (keep_src[j] >= L + j, so a row is always read before a later move can overwrite it).  No-op for chains.
+__device__ __noinline__ void stage_kv_compact(const DecModel* m, int cta, int ncta) {
+  const DecState* st = m->st;
+  const int keep = ldcg_i(&st->keep_n);   // (written by CTA 0 in the previous stage: L2-coherent reads; uniform across the grid)
+  if (keep <= 1) return;
+  const int d = m->d;
+  const int n_l = m->n_layers + (m->has_block ? 1 : 0);
+  const int L0 = ldcg_i(&st->keep_src[0]);   // = old L (node 0 is the root)
+  for (int item = cta; item < 2 * n_l; item += ncta) {
+    __half* base = (item & 1) ? m->layers[item >> 1].self_v : m->layers[item >> 1].self_k;
+    for (int j = 1; j < keep; ++j) {
+      const int src = ldcg_i(&st->keep_src[j]), dst = L0 + j;
+      if (src != dst) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(base + (size_t)src * d);
+        uint4* d4 = reinterpret_cast<uint4*>(base + (size_t)dst * d);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        const bool on = threadIdx.x < d / 8;
+        if (on) v = ldcg_u4(s4 + threadIdx.x);
+        cta_sync();
+        if (on) d4[threadIdx.x] = v;
+      }
+      cta_sync();
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------------
 // GEMM descriptors of the stages
 // -----------------------------------------------------------------------------------------
 enum StageId {
   ST_EMBED = 0, ST_QKV, ST_SELF_ATTN, ST_OPROJ, ST_CROSS_Q, ST_CROSS_ATTN, ST_CROSS_O,
   ST_FC1, ST_FC2, ST_FINAL_LN, ST_COPY_HIDDEN, ST_TAIL_SEED, ST_HEADS, ST_VOCAB, ST_SELECT1, ST_SELECT2, ST_SELECT_FIN,
-  ST_ACCEPT
+  ST_ACCEPT, ST_KV_COMPACT
 };
 enum PhaseId { PH_SWEEP_A = 0, PH_TAIL = 1, PH_VERIFY = 2 };
 
@@ -1097,7 +1300,7 @@ __host__ __device__ GemmDesc make_gemm_desc(const DecModel* m, int stage, int mo
     case ST_VOCAB:
     default:
       g.W = m->embed; g.N = m->V; g.K = d;
-      g.xsrc = XS_PLAIN; g.X = m->head_h; g.x_rows = m->K + 1;
+      g.xsrc = XS_PLAIN; g.X = m->head_h; g.x_rows = (mode == MODE_A) ? m->K + 1 : m->n_tree;
       g.epi = EPI_LOGITS; g.out = (mode == MODE_A) ? m->logits_a : m->logits_b; g.ldo = m->V;
       break;
   }
@@ -1119,7 +1322,10 @@ __device__ void run_stage(const DecModel* m, int stage, int mode, int layer, int
     case ST_SELECT1: stage_select1(m, mode, cta, ncta, smem); break;
     case ST_SELECT2: stage_select2(m, cta, ncta, smem); break;
     case ST_SELECT_FIN: if (cta == 0) stage_select_fin(m, ncta); break;
-    case ST_ACCEPT: if (cta == 0) stage_accept(m, ncta); break;
+    case ST_ACCEPT:
+      if (cta == 0) { if (m->has_tree) stage_accept_tree(m, ncta); else stage_accept(m, ncta); }
+      break;
+    case ST_KV_COMPACT: if (m->has_tree) stage_kv_compact(m, cta, ncta); break;
     default:
       if (WITH_GEMM) {
         GemmDesc g = make_gemm_desc(m, stage, mode, layer, gopt);
@@ -1157,6 +1363,7 @@ __host__ __device__ void seq_verify(int n_layers, int has_block, F&& f) {
   seq_sweep(n_layers, has_block, MODE_B, f);
   if (!has_block) f(ST_HEADS, MODE_B, 0);
   f(ST_VOCAB, MODE_B, 0); f(ST_SELECT1, MODE_B, 0); f(ST_SELECT2, MODE_B, 0); f(ST_ACCEPT, MODE_B, 0);
+  f(ST_KV_COMPACT, MODE_B, 0);   // (returns at once unless a candidate tree is configured)
 }
 
 // -----------------------------------------------------------------------------------------
@@ -1415,6 +1622,7 @@ static int stage_grid(int stage, int T, int n_sm, int H, int K) {
     case ST_TAIL_SEED: return 2;
     case ST_SELECT_FIN: return 1;
     case ST_ACCEPT: return 1;
+    case ST_KV_COMPACT: return 2 * WM_MAX_DEC_LAYERS;
     default: return n_sm;
   }
 }
@@ -1425,7 +1633,7 @@ static int stage_grid(int stage, int T, int n_sm, int H, int K) {
 //   PH_VERIFY : sweep B + acceptance
 cudaError_t dec_enqueue_phase(const DecModel* dm, const DecHostInfo& hi, int phase, int T, cudaStream_t s, int64_t* n_launch) {
   auto launch = [&](int stage, int mode, int layer) {
-    const int rows = (mode == MODE_B) ? hi.K + 1 : (mode == MODE_TAIL ? 1 : T);
+    const int rows = (mode == MODE_B) ? hi.n_tree : (mode == MODE_TAIL ? 1 : T);
     const int grid = stage_grid(stage, rows, hi.n_sm, hi.H, hi.K);
     dec_stage_kernel<<<grid, WM_DEC_THREADS, hi.smem, s>>>(dm, stage, mode, layer, phase);
     if (n_launch) ++*n_launch;

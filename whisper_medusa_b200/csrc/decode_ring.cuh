@@ -600,7 +600,7 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
     // the pass geometry derives from (L0, kv0, K): the loop state only changes in the very last stage
     PassGeom pgv;
     if (mode == MODE_A) { pgv.T = L0 - kv0; pgv.base = kv0; }
-    else if (mode == MODE_B) { pgv.T = m->K + 1; pgv.base = L0; }
+    else if (mode == MODE_B) { pgv.T = m->n_tree; pgv.base = L0; }
     else { pgv.T = 1; pgv.base = L0 - 1; }
     if (is_gemm_stage(stage)) {
       stage_gemm_ring<D>(rs, smem, m, sd, pgv.T, pgv.base, pr);

@@ -66,6 +66,7 @@ struct wm_handle {
   ChunkDesc* chunk_tab = nullptr;
   int* chunk_off = nullptr;
   CtaStage* stage_tab = nullptr;
+  DecTree* tree = nullptr;       // device copy of the candidate tree (branching medusa_choices)
   DecHostInfo hi;
   std::map<int, cudaGraphExec_t> graph_a;  // sweep A, keyed by T
   cudaGraphExec_t graph_tail = nullptr, graph_b = nullptr;
@@ -286,6 +287,9 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   memset(&m, 0, sizeof m);
   m.d = (int)d; m.H = c.n_heads; m.ffn = (int)f; m.V = (int)V; m.S = h->S; m.S_pad = h->S_pad;
   m.n_layers = c.dec_layers; m.has_block = c.medusa_block ? 1 : 0; m.K = c.medusa_num_heads;
+  m.n_tree = c.medusa_num_heads + 1; m.has_tree = 0; m.tree = nullptr;
+  CK(dalloc(&h->tree, 1));
+  CK(dalloc(&m.topk_part, (size_t)WM_MAX_T * 32 * WM_TREE_MAX_TOPK * 2));
   CK(dalloc(&m.x, (size_t)WM_MAX_T * d));
   CK(dalloc(&m.q, (size_t)WM_MAX_T * d));
   CK(dalloc(&m.attn, (size_t)WM_MAX_T * d));
@@ -315,6 +319,7 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
 
   h->hi.n_sm = h->n_cta; h->hi.H = c.n_heads; h->hi.K = c.medusa_num_heads; h->hi.n_layers = c.dec_layers;
   h->hi.has_block = m.has_block;
+  h->hi.n_tree = m.n_tree;
   h->hi.d = (int)d;
   h->hi.smem = dec_smem_bytes((int)d, (int)f);
   h->hi.smem_ring = dec_ring_smem_bytes((int)d);
@@ -353,7 +358,7 @@ extern "C" int wm_destroy(wm_handle* h) {
   for (auto p : h->self_k) F(p);
   for (auto p : h->self_v) F(p);
   F(h->hm.x); F(h->hm.q); F(h->hm.attn); F(h->hm.ffn_h); F(h->hm.hidden); F(h->hm.head_h); F(h->hm.carry); F(h->hm.cross_part); F(h->hm.cross_cnt); F(h->hm.sel_part); F(h->hm.gemm_part); F(h->hm.gemm_cnt);
-  F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->prog); F(h->prof); F(h->chunk_tab); F(h->chunk_off); F(h->stage_tab); F(h->dm);
+  F(h->hm.topk_part); F(h->tree); F(h->hm.logits_a); F(h->hm.logits_b); F(h->st); F(h->tok_mask); F(h->pen_tab); F(h->bar); F(h->prog); F(h->prof); F(h->chunk_tab); F(h->chunk_off); F(h->stage_tab); F(h->dm);
   if (h->wowned) F(h->wdev);
   if (h->h_state) cudaFreeHost(h->h_state);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -462,6 +467,64 @@ extern "C" int wm_adopt_weights(wm_handle* h, void* device_blob, size_t nbytes) 
   h->wdev = reinterpret_cast<unsigned char*>(device_blob);
   h->wowned = false;
   return bind_weights(h);
+}
+
+// Candidate tree of branching medusa_choices (reference medusa_utils.py:305-421, restated): choices[i] = how many of
+// head i's top tokens are tried at depth i (choices[0] = 1: the base head's argmax).  All ones = the top-1 chain.
+extern "C" int wm_set_medusa_choices(wm_handle* h, const int32_t* choices, int32_t n) {
+  if (!h || !choices) return WM_ERR_INVALID;
+  if (h->device < 0) return fail(h, WM_ERR_STATE, "layout-only handle");
+  const int K = h->cfg.medusa_num_heads;
+  if (n != K + 1) return fail(h, WM_ERR_INVALID, "medusa_choices must have medusa_num_heads + 1 entries");
+  if (choices[0] != 1) return fail(h, WM_ERR_INVALID, "medusa_choices[0] must be 1 (the base head is greedy)");
+  static thread_local DecTree t;
+  memset(&t, 0, sizeof t);
+  bool chain = true;
+  long n_tree = 0, level = 1;
+  for (int i = 0; i <= K; ++i) {
+    if (choices[i] < 1 || choices[i] > WM_TREE_MAX_TOPK) return fail(h, WM_ERR_UNSUPPORTED, "medusa_choices entries must be in 1..4");
+    if (choices[i] != 1) chain = false;
+    level *= choices[i];
+    n_tree += level;
+    if (n_tree > WM_MAX_T || level > WM_TREE_MAX_CAND)
+      return fail(h, WM_ERR_UNSUPPORTED, "candidate tree too large for this engine (at most 16 nodes and 32 paths)");
+  }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  DecModel& m = h->hm;
+  if (chain) {
+    m.has_tree = 0; m.tree = nullptr; m.n_tree = K + 1;
+  } else {
+    t.n_tree = (int)n_tree; t.n_cand = (int)level;
+    // nodes level by level; the node with in-level index q at depth i has parent q / choices[i] and carries the
+    // (q % choices[i])-th best token of head i (tree_indices repeats each level's top-k block)
+    int start = 0, prev_start = 0, size = 1;
+    for (int i = 0; i <= K; ++i) {
+      if (i > 0) size *= choices[i];
+      for (int q = 0; q < size; ++q) {
+        const int node = start + q;
+        t.depth[node] = i;
+        t.rank[node] = q % choices[i];
+        t.parent[node] = (i == 0) ? -1 : prev_start + q / choices[i];
+        t.anc[node] = (1u << node) | (i == 0 ? 0u : t.anc[t.parent[node]]);
+      }
+      t.topk[i] = choices[i];
+      // retrieve_indices[:, i]: path c passes through in-level node c / (n_cand / size)
+      for (int c = 0; c < t.n_cand; ++c) t.retrieve[c][i] = start + c / (t.n_cand / size);
+      prev_start = start;
+      start += size;
+    }
+    CK(cudaMemcpy(h->tree, &t, sizeof t, cudaMemcpyHostToDevice));
+    m.has_tree = 1; m.tree = h->tree; m.n_tree = t.n_tree;
+  }
+  h->hi.n_tree = m.n_tree;
+  for (auto& kv : h->graph_a) cudaGraphExecDestroy(kv.second);
+  h->graph_a.clear();
+  if (h->graph_b) { cudaGraphExecDestroy(h->graph_b); h->graph_b = nullptr; }
+  if (h->graph_tail) { cudaGraphExecDestroy(h->graph_tail); h->graph_tail = nullptr; }
+  if (h->wready) return bind_weights(h);   // the stage records of the verify vocabulary projection carry the row count
+  CK(cudaMemcpy(h->dm, &m, sizeof m, cudaMemcpyHostToDevice));
+  return WM_OK;
 }
 
 extern "C" int wm_set_suppress(wm_handle* h, const int32_t* sup, int32_t n_sup, const int32_t* beg, int32_t n_beg) {
@@ -663,6 +726,7 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
     hs.max_length = gp->max_length; hs.eos = gp->eos_token_id; hs.pad = gp->pad_token_id;
     hs.begin_index = gp->begin_index; hs.temperature = gp->temperature; hs.post_thr = gp->posterior_threshold;
     hs.post_alpha = gp->posterior_alpha;
+    hs.tree_attn = (h->hm.has_tree && gp->tree_attention) ? 1 : 0;
     for (int i = 0; i < n_prompt; ++i) hs.ids[i] = prompt[i];
     // reference stop rule evaluated before the first iteration is never true for sane inputs; the
     // loop always runs at least once (model.py:635).
@@ -678,7 +742,7 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
     if ((r = get_graph(h, 0, n_prompt, &gAp, &nAp)) != WM_OK) return r;
     if ((r = get_graph(h, 0, 1, &gA1, &nA1)) != WM_OK) return r;
     if ((r = get_graph(h, 1, 1, &gT, &nT)) != WM_OK) return r;
-    if ((r = get_graph(h, 2, K + 1, &gB, &nB)) != WM_OK) return r;
+    if ((r = get_graph(h, 2, h->hm.n_tree, &gB, &nB)) != WM_OK) return r;
   }
   CK(cudaEventRecord(h->ev[3], s));
   int L = n_prompt, iters = 0, done = 0;

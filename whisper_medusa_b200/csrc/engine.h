@@ -13,6 +13,7 @@ struct DecModel;
 struct DecHostInfo {
   int n_sm;
   int H, K, n_layers, has_block;
+  int n_tree;      // rows of the verify pass (K + 1 for the chain)
   int d;
   size_t smem;
   size_t smem_ring;

@@ -93,10 +93,6 @@ class WhisperMedusaModel:
         self._device: Optional[torch.device] = None
         self._wblob_dev: Optional[torch.Tensor] = None
         self.last_trace = GenerateTrace()
-        if config.medusa_choices and any(int(c) != 1 for c in config.medusa_choices):
-            raise NotImplementedError(
-                "the CUDA engine implements top-1 chains (medusa_choices all 1), the only configuration "
-                "the reference ships (README.md:181); branching choices are listed under 'next' in DESIGN.md")
         if len(config.medusa_choices) != config.medusa_num_heads + 1:
             raise ValueError("len(medusa_choices) must be medusa_num_heads + 1")
 
@@ -204,6 +200,14 @@ class WhisperMedusaModel:
             self._wblob_dev = dev_blob  # keep alive: the engine does not own it
             _check(lib, handle, lib.wm_adopt_weights(handle, C.c_void_p(dev_blob.data_ptr()), nbytes), "wm_adopt_weights")
         self._push_suppress()
+        # candidate tree (all ones = the top-1 chain the reference ships, README.md:181; branching choices: per-head
+        # top-k + tree verify, medusa_utils.py:305-458 -- the engine holds trees of <= 16 nodes / 32 paths / k <= 4)
+        ch = [int(c) for c in self.config.medusa_choices]
+        arr = (C.c_int32 * len(ch))(*ch)
+        rc = lib.wm_set_medusa_choices(handle, arr, len(ch))
+        if rc == -4:
+            raise NotImplementedError(f"medusa_choices {ch}: {lib.wm_last_error(handle).decode()}")
+        _check(lib, handle, rc, "wm_set_medusa_choices")
         return self
 
     def cuda(self, index: int = 0) -> "WhisperMedusaModel":
@@ -300,7 +304,7 @@ class WhisperMedusaModel:
             posterior_alpha=float(g.posterior_alpha),
             penalty_start=int(pen[0]) if pen is not None else -1,
             penalty_factor=float(pen[1]) if pen is not None else 1.0,
-            max_iters=int(max_iters or 0))
+            max_iters=int(max_iters or 0), tree_attention=0)
 
     def _run_loop(self, prompt: Sequence[int], gp: _lib.WmGenParams) -> GenerateTrace:
         lib = _lib.load()
@@ -395,7 +399,7 @@ class WhisperMedusaModel:
             # _multi_heads_generate has no sampling branch (model.py:1130-1156)
             raise NotImplementedError("sampling (temperature > 0 / do_sample) is not supported with medusa: greedy search only")
         known = {"exponential_decay_length_penalty", "max_length", "max_new_tokens", "max_iters", "medusa_temperature",
-                 "posterior_threshold", "posterior_alpha", "num_beams", "do_sample", "use_cache"}
+                 "posterior_threshold", "posterior_alpha", "num_beams", "do_sample", "use_cache", "tree_attention"}
         unknown = sorted(set(kwargs) - known)
         if unknown:
             raise NotImplementedError(f"generate() options not implemented by the B200 engine: {unknown}")
@@ -434,6 +438,9 @@ class WhisperMedusaModel:
             gp.posterior_threshold = float(kwargs.pop("posterior_threshold"))
         if kwargs.get("posterior_alpha") is not None:
             gp.posterior_alpha = float(kwargs.pop("posterior_alpha"))
+        # branching medusa_choices: False (default) = the reference's behaviour (its medusa_attn_mask is built but never
+        # applied: verify rows attend causally over cache order); True = every node attends to its ancestors only
+        gp.tree_attention = 1 if kwargs.pop("tree_attention", False) else 0
         tr = self._run_loop(prompt, gp)
         self.last_trace = tr
         out = self._strip(tr.sequences, len(prompt), int(gp.pad_token_id), int(gp.eos_token_id))
