@@ -44,8 +44,12 @@ def _newer(src_paths: List[str], target: str) -> bool:
     return any(os.path.getmtime(p) > t for p in src_paths)
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
-    os.makedirs(OBJ_DIR, exist_ok=True)
+def build(verbose: bool = False, force: bool = False, extra_flags: List[str] = (), lib_path: str = LIB_PATH,
+          obj_dir: str = OBJ_DIR) -> str:
+    """``extra_flags`` / ``lib_path`` / ``obj_dir``: alternative builds for A/B timing (tests/gpu_ab.py), e.g.
+    ``build(extra_flags=["-DWM_EPI_PIPELINE=1"], lib_path="ab_libs/v1.so", obj_dir="ab_libs/obj_v1")``."""
+    os.makedirs(obj_dir, exist_ok=True)
+    os.makedirs(os.path.dirname(os.path.abspath(lib_path)), exist_ok=True)
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(ROOT, "include", "whisper_medusa_b200.h"))
@@ -53,10 +57,10 @@ def build(verbose: bool = False, force: bool = False) -> str:
 
     def compile_one(src: str):
         sp = os.path.join(CSRC, src)
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         if not force and not _newer([sp] + headers, obj):
             return obj, ""
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-c", sp, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-c", sp, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -71,12 +75,12 @@ def build(verbose: bool = False, force: bool = False) -> str:
             f.write(log + "\n")
         if verbose:
             print(log)
-    if force or _newer(objs, LIB_PATH):
-        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    if force or _newer(objs, lib_path):
+        cmd = [nvcc, "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

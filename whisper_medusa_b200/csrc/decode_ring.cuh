@@ -385,20 +385,25 @@ __device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* sm
   } else {
     const int etid = tid - G::NKS * 32;
     constexpr int NOUT = (256 + NE - 1) / NE;   // outputs per epilogue thread and unit
-    for (int u = 0; u < units; ++u) {
+    // this thread's bias / residual values of a unit are requested before its partials are awaited: the loads are in
+    // flight while the MMA warps work
+    float bias_v[NOUT], old[NOUT];
+    auto fetch = [&](int u, float* bv, float* ov) {
       const int nvalid = min(16, n_rows - u * 16);
-      // this thread's outputs of the unit; their bias / residual loads are in flight while the MMA warps work
-      float bias_v[NOUT], old[NOUT];
 #pragma unroll
       for (int k = 0; k < NOUT; ++k) {
         const int o = etid + k * NE, token = o >> 4, rloc = o & 15;
-        bias_v[k] = 0.f; old[k] = 0.f;
+        bv[k] = 0.f; ov[k] = 0.f;
         if (o < 256 && token < T && rloc < nvalid && !ksplit) {
           const float* bias = sd->bias;
-          if (bias) bias_v[k] = bias[n_begin + u * 16 + rloc];
-          if (epi == EPI_RESID) old[k] = ldcg_f(&sd->out[(size_t)token * sd->ldo + n_begin + u * 16 + rloc]);
+          if (bias) bv[k] = bias[n_begin + u * 16 + rloc];
+          if (epi == EPI_RESID) ov[k] = ldcg_f(&sd->out[(size_t)token * sd->ldo + n_begin + u * 16 + rloc]);
         }
       }
+    };
+    fetch(0, bias_v, old);
+    for (int u = 0; u < units; ++u) {
+      const int nvalid = min(16, n_rows - u * 16);
       asm volatile("bar.sync 2, %0;" ::"n"(WM_DEC_THREADS) : "memory");   // partials of unit u are written
       float sum[NOUT];
 #pragma unroll
@@ -446,6 +451,7 @@ __device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* sm
           out[(size_t)token * ldo + row] = xbuf_value(xb, G::XS, token, row) + silu(s + bias_v[k]);
         }
       }
+      if (u + 1 < units) fetch(u + 1, bias_v, old);   // (A/B round 2: fetching TWO units ahead into a second register set was slower, 1.932 vs 1.905 ms)
     }
     for (int u = 0; u < units; ++u)
       if (++rs.slot == WM_RING_G) { rs.slot = 0; rs.par ^= 1u; }   // keep the (uniform) ring state in step with the MMA warps
