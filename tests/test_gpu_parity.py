@@ -453,7 +453,7 @@ def test_branching_trees_both_attention_modes(htype, heads, choices):
         for temp in (1.0, 0.0):
             gp = M.gen_params(cfg, prompt, None, 100, temperature=temp)
             for tree_attn in (False, True):
-                for mode in ("persistent", "graph"):
+                for mode in (("persistent", "graph") if (seed == 2 and temp == 1.0) else ("persistent",)):
                     m.set_decode_mode(mode)
                     m.generate_from_pcm(pcm, max_length=100, medusa_temperature=temp, tree_attention=tree_attn)
                     tr = M.medusa_greedy_search(w, cfg, enc, prompt, gp, "engine", tree_attention=tree_attn)
