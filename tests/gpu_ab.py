@@ -37,6 +37,9 @@ def main():
         try:
             model = WhisperMedusaModel(cfg, sd).to("cuda:0")
             model.set_decode_mode("persistent")
+            for kv in [o for o in os.environ.get("WM_AB_OPTS", "").split(",") if o]:      # e.g. WM_AB_OPTS=iters_per_launch=1
+                k, v = kv.split("=")
+                model.set_option(k, int(v))
             times, ok = [], True
             for r in range(reps + 1):
                 out = model.generate_from_pcm(pcm, **kw)[0].tolist()

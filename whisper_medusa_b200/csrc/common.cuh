@@ -217,7 +217,7 @@ struct DecState {
   float row_thr[WM_MAX_T];
 };
 
-struct DecModel {
+struct alignas(16) DecModel {   // (copied to shared memory in 16-byte pieces by the ring kernel)
   int d, H, ffn, V, S, S_pad;
   int n_layers;      // decoder layers (without the medusa block)
   int has_block;     // 1 => layers[n_layers] is the medusa block

@@ -564,7 +564,7 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
   {
     const int4* src = reinterpret_cast<const int4*>(gm);
     int4* dst = reinterpret_cast<int4*>(sm);
-    // (the device copy of DecModel is allocated in 256-byte granules: reading up to the next 16 B is safe)
+    // (sizeof(DecModel) is a multiple of 16: alignas(16))
     for (int i = threadIdx.x; i < (int)((sizeof(DecModel) + 15) / 16); i += WM_RING_THREADS) dst[i] = src[i];
   }
   __syncthreads();   // the only full-CTA barrier: after it the producer warp goes its own way
