@@ -188,8 +188,8 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     for (int cb = (warp - 2) >> 2; cb < BN / 32; cb += 2) {
       uint32_t v[32];
       tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
-      if (!row_ok) continue;
       const int col0 = n0 + cb * 32;
+      if ((EPI == ENC_EPI_BIAS_F16 || EPI == ENC_EPI_BIAS_GELU_F16) && !row_ok) continue;   // (fp32 epilogues: warp-cooperative)
       if (EPI == ENC_EPI_BIAS_F16 || EPI == ENC_EPI_BIAS_GELU_F16) {
         __half* dst = a.out16 + (size_t)row * a.ldo16 + col0;
 #pragma unroll
@@ -205,22 +205,37 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           *reinterpret_cast<uint4*>(dst + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       } else {
-        float* dst = a.out32 + (size_t)row * a.ldo32 + col0;
+        // fp32 read-modify-write epilogues (residual stream / conv2 + positions).  tcgen05.ld hands every thread one ROW
+        // of the tile; row-wise global accesses would touch 32 different lines per instruction (the kernel then spends
+        // most of its time waiting for the residual loads -- ncu, round 2).  The 32 x 32 block is transposed through
+        // shared memory (the pipeline stages are idle once the accumulator is complete): lane = column, so every
+        // load / store of the residual stream is one contiguous 128-byte segment.
+        float* sC = reinterpret_cast<float*>(smem_raw) + (size_t)(warp - 2) * (32 * 33);
+        __syncwarp();
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float4 o;
-          float x0 = __uint_as_float(v[c4 * 4 + 0]) + a.bias[col0 + c4 * 4 + 0];
-          float x1 = __uint_as_float(v[c4 * 4 + 1]) + a.bias[col0 + c4 * 4 + 1];
-          float x2 = __uint_as_float(v[c4 * 4 + 2]) + a.bias[col0 + c4 * 4 + 2];
-          float x3 = __uint_as_float(v[c4 * 4 + 3]) + a.bias[col0 + c4 * 4 + 3];
-          if (EPI == ENC_EPI_BIAS_RES_F32) {
-            const float4 r = *reinterpret_cast<const float4*>(dst + c4 * 4);
-            o = make_float4(r.x + x0, r.y + x1, r.z + x2, r.w + x3);
-          } else {
-            const float4 pz = *reinterpret_cast<const float4*>(a.pos + (size_t)row * a.N + col0 + c4 * 4);
-            o = make_float4(gelu_erf(x0) + pz.x, gelu_erf(x1) + pz.y, gelu_erf(x2) + pz.z, gelu_erf(x3) + pz.w);
+        for (int c = 0; c < 32; ++c) sC[lane * 33 + c] = __uint_as_float(v[c]);
+        __syncwarp();
+        const float bcol = a.bias[col0 + lane];
+        const int row_base = m0 + q * 32;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+          float in[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = row_base + r0 + i;
+            in[i] = 0.f;
+            if (rr < a.M)
+              in[i] = (EPI == ENC_EPI_BIAS_RES_F32) ? a.out32[(size_t)rr * a.ldo32 + col0 + lane]
+                                                    : a.pos[(size_t)rr * a.N + col0 + lane];
           }
-          *reinterpret_cast<float4*>(dst + c4 * 4) = o;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = row_base + r0 + i;
+            if (rr < a.M) {
+              const float x = sC[(r0 + i) * 33 + lane] + bcol;
+              a.out32[(size_t)rr * a.ldo32 + col0 + lane] = (EPI == ENC_EPI_BIAS_RES_F32) ? in[i] + x : gelu_erf(x) + in[i];
+            }
+          }
         }
       }
     }
