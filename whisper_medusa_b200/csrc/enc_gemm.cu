@@ -159,23 +159,49 @@ cudaError_t enc_gemm(const EncGemmArgs& a, cudaStream_t s, int64_t* n_launch) {
 // ---------------------------------------------------------------------------------------------
 // LayerNorm (eps 1e-5, biased variance): one warp per row; writes the fp16 GEMM operand
 // ---------------------------------------------------------------------------------------------
-__global__ void enc_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
-                                     __half* __restrict__ y16, float* __restrict__ y32, int M, int d) {
+// The row (d <= 1280, a multiple of 128) is read ONCE with 16-byte loads and kept in registers for the two-pass
+// statistics and the normalisation; outputs are written as 8-byte (fp16) / 16-byte (fp32) vectors.
+__global__ void __launch_bounds__(256) enc_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                            const float* __restrict__ b, __half* __restrict__ y16,
+                                                            float* __restrict__ y32, int M, int d) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  const float* xr = x + (size_t)row * d;
+  const int nv = d >> 7;                       // float4 per lane
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d) + lane;
+  float4 v[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    if (i < nv) v[i] = xr[i * 32];
   float s = 0.f;
-  for (int j = lane; j < d; j += 32) s += xr[j];
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) / (float)d;
-  float v = 0.f;
-  for (int j = lane; j < d; j += 32) { const float dl = xr[j] - mean; v += dl * dl; }
-  const float rstd = rsqrtf(warp_sum(v) / (float)d + 1e-5f);
-  for (int j = lane; j < d; j += 32) {
-    const float y = (xr[j] - mean) * rstd * g[j] + b[j];
-    y16[(size_t)row * d + j] = __float2half_rn(y);
-    if (y32) y32[(size_t)row * d + j] = y;
-  }
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    if (i < nv) {
+      const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(g) + lane;
+  const float4* b4 = reinterpret_cast<const float4*>(b) + lane;
+  uint2* o16 = reinterpret_cast<uint2*>(y16 + (size_t)row * d) + lane;
+  float4* o32 = y32 ? reinterpret_cast<float4*>(y32 + (size_t)row * d) + lane : nullptr;
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    if (i < nv) {
+      const float4 gg = g4[i * 32], bb = b4[i * 32];
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * gg.x + bb.x;
+      y.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+      y.z = (v[i].z - mean) * rstd * gg.z + bb.z;
+      y.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+      o16[i * 32] = make_uint2(pack_half2(y.x, y.y), pack_half2(y.z, y.w));
+      if (o32) o32[i * 32] = y;
+    }
 }
 
 cudaError_t enc_layernorm(const float* x, const float* g, const float* b, __half* y16, float* y32, int M, int d,
