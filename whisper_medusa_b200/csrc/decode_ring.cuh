@@ -222,6 +222,53 @@ __device__ __forceinline__ float xbuf_value(const unsigned char* xb, int xs, int
   return __half2float(p[0]) + __half2float(p[2]);
 }
 
+#ifndef WM_LN_MODE
+#define WM_LN_MODE 1
+#endif
+#if WM_LN_MODE == 2
+#define WM_LN_INLINE __noinline__
+#else
+#define WM_LN_INLINE __forceinline__
+#endif
+// LayerNorm of the landed activation rows, ONE pass: warp per row, the row lives in registers (lane l holds float4
+// columns l, l+32, ...: the summation order of the two-pass statistics is unchanged), normalised with gamma / beta from
+// the shared parameter buffer and written back in the fp16 hi/lo operand format.
+template <int D>
+__device__ WM_LN_INLINE void ring_layernorm_rows(unsigned char* xb, const float* partial, int T) {
+  using G = RingGeom<D>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nwarps = WM_DEC_THREADS >> 5;
+  for (int r = warp; r < T; r += nwarps) {
+    uint4* row = reinterpret_cast<uint4*>(xb + (size_t)r * G::XS) + lane;
+    float4 v[G::NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < G::NV; ++i)
+      if (i * 32 + lane < G::NV4) { v[i] = *reinterpret_cast<const float4*>(row + i * 32); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < G::NV; ++i)
+      if (i * 32 + lane < G::NV4) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + e * e);
+      }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < G::NV; ++i)
+      if (i * 32 + lane < G::NV4) {
+        const float4 gg = reinterpret_cast<const float4*>(partial)[i * 32 + lane];
+        const float4 bb = reinterpret_cast<const float4*>(partial)[G::NV4 + i * 32 + lane];
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * gg.x + bb.x;
+        y.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+        y.z = (v[i].z - mean) * rstd * gg.z + bb.z;
+        y.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+        row[i * 32] = split_hilo4(y);
+      }
+  }
+}
+
 // per-thread state of the compute warps that survives across stages (uniform over the CTA)
 struct RingState {
   int slot;            // ring slot of the next chunk to consume
@@ -277,6 +324,15 @@ __device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* sm
   while (!mbar_try_wait(xbar, rs.xpar)) { }
   rs.xpar ^= 1u;
   if (pr) pr[8] = global_timer_ns();
+#if WM_LN_MODE != 0
+  if (ln) {
+    // gamma / beta were bulk-copied into the (idle) partial buffer during the preceding barrier
+    while (!mbar_try_wait(pbar, rs.ppar)) { }
+    rs.ppar ^= 1u;
+    if (pr) pr[9] = global_timer_ns();
+    ring_layernorm_rows<D>(xb, partial, T);
+  } else
+#else
   if (ln) {
     // statistics: one warp per row, lane l sums float4 columns l, l+32, ... (two passes over shared memory)
     for (int r = warp; r < T; r += nwarps) {
@@ -317,7 +373,9 @@ __device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* sm
         *p = split_hilo4(y);
       }
     }
-  } else if (!sd->presplit) {
+  } else
+#endif
+  if (!sd->presplit) {
     // flat over the buffer (the 16-byte row pad is converted along: no index arithmetic)
     uint4* p = reinterpret_cast<uint4*>(xb);
     const int n16 = T * (G::XS >> 4);
