@@ -45,6 +45,9 @@ CASES = {
     "large_linear_k6_mixed": ("large-v2", 6, "base_head", 0, 30.0, 1, 130, None, 1.0, 100.0, 0.09),
     "large_linear_k4_mixed": ("large-v2", 4, "base_head", 0, 30.0, 2, 110, None, 1.0, 100.0, 0.09),
     "large_linear_k2_mixed": ("large-v2", 2, "base_head", 0, 30.0, 3, 90, None, 1.0, 100.0, 0.09),
+    # Block heads of the synthetic model are uncorrelated with the base model (ratio p*e^H ~ 0.02 / 0.015 / 0.004 ...):
+    # alpha = 0.016 accepts the first one or two positions => the block's carry / tail path with accept >= 1 at d = 1280
+    "large_block_k10_mixed": ("large-v2", 10, "medusa_block", 0, 30.0, 0, 110, None, 1.0, 0.016, 0.09),
     # alpha = 230 also fails the first chain position about half of the time: accept-0 iterations (two emitted
     # tokens, the extra one-token sweep) interleaved with accepting ones
     # (stream 5 of a small search over streams 4-7 x alpha 210/230/250: the only one with accept-0 iterations whose

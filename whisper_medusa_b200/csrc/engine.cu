@@ -51,7 +51,7 @@ struct wm_handle {
   // encoder buffers
   float *pcm = nullptr, *mel32 = nullptr, *melfb = nullptr, *x32 = nullptr, *enc32 = nullptr;
   __half *x_tm = nullptr, *h1 = nullptr, *ln16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *ffn16 = nullptr,
-         *enc16 = nullptr;
+         *enc16 = nullptr, *vt16 = nullptr;
   int* gmax = nullptr;
   std::vector<__half*> cross_k, cross_v, self_k, self_v;
   // decode buffers
@@ -74,7 +74,8 @@ struct wm_handle {
   int64_t launches_tail = 0, launches_b = 0;
   int decode_mode = 0;
   int enc_gemm_impl = 0;   // 0 = mma.sync kernel, 1 = tcgen05/TMA kernel
-  bool tc_ok = false;
+  int enc_attn_impl = 0;   // 0 = mma.sync flash attention, 1 = tcgen05/TMA/TMEM attention
+  bool tc_ok = false, attn_tc_ok = false;
   bool encoded = false;
   // pinned staging + timing
   int* h_state = nullptr;  // pinned copy of the DecState header
@@ -268,6 +269,7 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   CK(dalloc(&h->att16, SP * d));
   CK(dalloc(&h->ffn16, SP * f));
   CK(dalloc(&h->enc16, SP * d));
+  CK(dalloc(&h->vt16, d * SP));
   h->cross_k.resize(h->n_dec);
   h->cross_v.resize(h->n_dec);
   h->self_k.resize(h->n_dec);
@@ -337,6 +339,8 @@ extern "C" int wm_create(const wm_config* cfg, int device, wm_handle** out) {
   CK(enc_gemm_configure());
   h->tc_ok = (enc_gemm_tc_configure() == cudaSuccess);
   h->enc_gemm_impl = h->tc_ok ? 1 : 0;   // tcgen05/TMA GEMM by default; option "enc_gemm" = 0 selects the mma.sync kernel
+  h->attn_tc_ok = (enc_attention_tc_configure() == cudaSuccess);
+  h->enc_attn_impl = h->attn_tc_ok ? 1 : 0;   // likewise option "enc_attn"
   (void)cudaGetLastError();
   if (!simple_modes_fit(h) && !h->hi.smem_ring) return fail(h, WM_ERR_UNSUPPORTED, "too few SMs for the vocab projection split");
   return WM_OK;
@@ -352,7 +356,7 @@ extern "C" int wm_destroy(wm_handle* h) {
   if (h->graph_tail) cudaGraphExecDestroy(h->graph_tail);
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(h->pcm); F(h->mel32); F(h->melfb); F(h->gmax); F(h->x_tm); F(h->h1); F(h->x32); F(h->enc32); F(h->ln16);
-  F(h->qkv16); F(h->att16); F(h->ffn16); F(h->enc16);
+  F(h->qkv16); F(h->att16); F(h->ffn16); F(h->enc16); F(h->vt16);
   for (auto p : h->cross_k) F(p);
   for (auto p : h->cross_v) F(p);
   for (auto p : h->self_k) F(p);
@@ -575,8 +579,11 @@ static int run_encoder(wm_handle* h) {
     memset(&a, 0, sizeof a);
     a.A = h->ln16; a.lda = d; a.W = wptr<__half>(h, p + "qkv_w"); a.bias = wptr<float>(h, p + "qkv_b");
     a.M = S; a.N = 3 * d; a.K = d; a.epi = ENC_EPI_BIAS_F16; a.out16 = h->qkv16; a.ldo16 = 3 * d;
+    const bool vt_fused = (h->enc_attn_impl == 1 && h->enc_gemm_impl == 1);   // the tcgen05 GEMM epilogue writes V^T too
+    if (vt_fused) { a.vt = h->vt16; a.vt_col0 = 2 * d; a.vt_ld = h->S_pad; }
     CK(gemm_dispatch(h, a, s, nl));
-    CK(enc_attention(h->qkv16, h->att16, S, d, c.n_heads, s, nl));
+    if (h->enc_attn_impl == 1) CK(enc_attention_tc(h->qkv16, h->vt16, h->att16, S, h->S_pad, d, c.n_heads, vt_fused, s, nl));
+    else CK(enc_attention(h->qkv16, h->att16, S, d, c.n_heads, s, nl));
     memset(&a, 0, sizeof a);
     a.A = h->att16; a.lda = d; a.W = wptr<__half>(h, p + "o_w"); a.bias = wptr<float>(h, p + "o_b");
     a.M = S; a.N = d; a.K = d; a.epi = ENC_EPI_BIAS_RES_F32; a.out32 = h->x32; a.ldo32 = d;
@@ -906,6 +913,12 @@ extern "C" int wm_set_option(wm_handle* h, const char* key, int32_t value) {
     if (value && !h->prof) CK(dalloc(&h->prof, (size_t)2 * h->hm.prog_off[3] * 16));
     h->hm.prof = value ? h->prof : nullptr;
     CK(cudaMemcpy(h->dm, &h->hm, sizeof(DecModel), cudaMemcpyHostToDevice));
+    return WM_OK;
+  }
+  if (k == "enc_attn") {
+    if (value == 1 && !h->attn_tc_ok) return fail(h, WM_ERR_UNSUPPORTED, "tcgen05 attention unavailable (cuTensorMapEncodeTiled not found)");
+    if (value < 0 || value > 1) return fail(h, WM_ERR_INVALID, "enc_attn must be 0 (mma.sync) or 1 (tcgen05)");
+    h->enc_attn_impl = value;
     return WM_OK;
   }
   if (k == "enc_gemm") {

@@ -54,6 +54,8 @@ struct EncGemmArgs {
   __half* out16; int ldo16;     // fp16 outputs
   float* out32; int ldo32;      // fp32 residual stream (+=) or plain store
   const float* pos;             // [M, N] added after GELU (conv2)
+  __half* vt; int vt_col0, vt_ld;   // tcgen05 GEMM, ENC_EPI_BIAS_F16 only: columns >= vt_col0 also written transposed
+                                    // (vt[col - vt_col0][row], row stride vt_ld): V^T for the tcgen05 attention
 };
 cudaError_t enc_gemm(const EncGemmArgs& a, cudaStream_t s, int64_t* n_launch);
 cudaError_t enc_gemm_configure();
@@ -68,5 +70,12 @@ cudaError_t enc_gemm_tc_configure();
 // ---- enc_attn.cu ----
 // qkv: fp16 [S_pad, 3d] (q pre-scaled | k | v); out: fp16 [S_pad, d]; full (non-causal) attention over S keys
 cudaError_t enc_attention(const __half* qkv, __half* out, int S, int d, int H, cudaStream_t s, int64_t* n_launch);
+
+// ---- enc_attn_tc.cu (tcgen05 + TMA + TMEM) ----
+// qkv as above; vt: scratch fp16 [d][S_pad] (V transposed, written here); out: fp16 [S_pad, d]
+// vt_ready: the QKV GEMM already wrote V^T (EncGemmArgs::vt); otherwise a transpose kernel runs first
+cudaError_t enc_attention_tc(const __half* qkv, __half* vt, __half* out, int S, int S_pad, int d, int H, bool vt_ready,
+                             cudaStream_t s, int64_t* n_launch);
+cudaError_t enc_attention_tc_configure();
 
 }  // namespace wm
