@@ -10,7 +10,7 @@
 //                 D = P_b V (M=128 N=64, 4 x K=16, P_b from shared memory) into a TMEM block-output buffer;
 //                 tcgen05.commit signals the softmax warps / frees the ring stage
 //   warps 2..9  : softmax      -- two threads per query row (TMEM lane quarter = warp % 4, 32 key columns / 32 output
-//                 dims each): tcgen05.ld of the scores, running max (halves exchanged through shared memory) / sum, P as
+//                 dims each): tcgen05.ld of the scores, running max / sum, P as
 //                 fp16 into a double-buffered shared tile in the UMMA K-major SWIZZLE_128B layout, O (32 fp32 registers)
 //                 rescaled and accumulated from D
 // V^T ([H*64][S_pad] fp16) is produced by enc_transpose_v_kernel so that both products use K-major operands.
@@ -49,7 +49,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t q_full, kv_full[AT_STAGES], kv_empty[AT_STAGES], s_full[2], p_full[2], d_full;
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_mx[2][2][AT_BQ];   // [block parity][column half][row]: partial row maxima (and, at the end, sums)
+  __shared__ float s_mx[2][AT_BQ];      // [column half][row]: the two partial row sums, exchanged once at the end
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, q0 = blockIdx.x * AT_BQ;
   const int nkb = (S + AT_BK - 1) / AT_BK;
@@ -146,9 +146,22 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int nvalid = S - kb * AT_BK - hsel * 32;   // existing keys among this thread's 32 columns
       const bool full_block = nvalid >= 32;            // uniform per warp: only the last key block is partial
+      // row maximum over all 64 columns: the partner's half is read from TMEM too (cheaper than a shared-memory exchange
+      // and a 256-thread barrier per block); this thread's own half stays in registers for the exponentials
       uint32_t sv[32];
-      at_ld32(tS0 + lane_off + (uint32_t)(b * 64 + hsel * 32), sv);
       float mx = -INFINITY;
+      {
+        const int nv_o = S - kb * AT_BK - (hsel ^ 1) * 32;
+        at_ld32(tS0 + lane_off + (uint32_t)(b * 64 + (hsel ^ 1) * 32), sv);
+        if (nv_o >= 32) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (c < nv_o) ? __uint_as_float(sv[c]) : -INFINITY);
+        }
+      }
+      at_ld32(tS0 + lane_off + (uint32_t)(b * 64 + hsel * 32), sv);
       if (full_block) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
@@ -156,9 +169,6 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
         for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (c < nvalid) ? __uint_as_float(sv[c]) : -INFINITY);
       }
-      s_mx[b][hsel][rloc] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mx = fmaxf(mx, s_mx[b][hsel ^ 1][rloc]);
       const float m_new = fmaxf(m_run, mx);
       const float alpha = at_ex2((m_run - m_new) * L2E);   // first block: 2^-inf = 0
       const float msc = m_new * L2E;
@@ -215,9 +225,9 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       for (int c = 0; c < 32; ++c) o[c] += __uint_as_float(dv[c]);
     }
     // the two halves of a row used the same running maxima: their sums add up
-    s_mx[0][hsel][rloc] = l_run;
+    s_mx[hsel][rloc] = l_run;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    l_run += s_mx[0][hsel ^ 1][rloc];
+    l_run += s_mx[hsel ^ 1][rloc];
     const int row = q0 + rloc;
     if (row < S) {
       const float inv = 1.0f / l_run;

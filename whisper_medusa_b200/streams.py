@@ -55,6 +55,7 @@ class StreamGroup:
         self.device = torch.device("cuda", index)
         self.last_traces: List[GenerateTrace] = []
         self.last_wall_s = 0.0
+        self.last_decode_phase_s = 0.0
 
     def close(self) -> None:
         for m in reversed(self.models):
@@ -72,7 +73,7 @@ class StreamGroup:
         for i in range(n):
             work.put(i)
 
-        def worker(model: WhisperMedusaModel):
+        def worker(model: WhisperMedusaModel, widx: int):
             # one host thread per engine: ctypes releases the GIL inside the C ABI calls, so the S loops enqueue and
             # wait concurrently; each engine owns its CUDA stream
             while True:
@@ -83,12 +84,13 @@ class StreamGroup:
                 try:
                     outs[i] = call(model, clips[i], kwargs)
                     traces[i] = model.last_trace
+                    traces[i].engine_index = widx
                 except BaseException as e:  # noqa: BLE001
                     errors.append(e)
                     return
 
         t0 = time.perf_counter()
-        threads = [threading.Thread(target=worker, args=(m,)) for m in self.models[: max(1, min(self.n_streams, n))]]
+        threads = [threading.Thread(target=worker, args=(m, k)) for k, m in enumerate(self.models[: max(1, min(self.n_streams, n))])]
         for t in threads:
             t.start()
         for t in threads:
@@ -97,6 +99,11 @@ class StreamGroup:
         if errors:
             raise errors[0]
         self.last_traces = traces  # type: ignore[assignment]
+        # length of the decode phase: the engines decode concurrently, each for the sum of its own loops' device times
+        busy: Dict[int, float] = {}
+        for t in traces:
+            busy[t.engine_index] = busy.get(t.engine_index, 0.0) + t.ms_decode  # type: ignore[union-attr]
+        self.last_decode_phase_s = max(busy.values()) / 1e3 if busy else 0.0
         return outs  # type: ignore[return-value]
 
     def generate_from_pcm(self, clips: Sequence[Union[np.ndarray, torch.Tensor]], **kwargs) -> List[torch.Tensor]:
