@@ -445,6 +445,11 @@ def test_stream_group_equals_single_stream_runs():
         assert got == want, S
         feats = torch.stack([torch.from_numpy(W.log_mel_spectrogram(c)) for c in clips[:3]])
         assert [o[0].tolist() for o in grp.generate(feats, **kw)] == want[:3]
+        # forward() (and with it language detection) works on a partial decode grid too
+        ids = torch.tensor([[cfg.decoder_start_token_id, cfg.no_timestamps_token_id, 11]])
+        lg_part = grp.models[-1].forward(input_features=feats[:1], decoder_input_ids=ids).logits.cpu().numpy()
+        lg_full = single.forward(input_features=feats[:1], decoder_input_ids=ids).logits.cpu().numpy()
+        assert _rel_err(lg_part, lg_full) < 1e-3
         assert all(t.launches_decode == t.iterations for t in grp.last_traces)
         grp.close()
 

@@ -809,8 +809,8 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
 
 // Stacked head logits of a teacher-forced decoder pass (reference WhisperMedusaModel.forward, model.py:1223-1347:
 // `logits` [K+1, batch 1, T, V]).  The loop kernels only ever need the heads at the LAST position, so this utility
-// entry runs the prefix ids[0..t) through sweep A + the candidate tail for t = 1..T (stage-kernel graphs; O(T^2) rows,
-// T <= 16) and collects the K+1 rows of each: out[(k * T + t) * V + v].  Raw logits, no processors.
+// entry runs the prefix ids[0..t) through sweep A + the candidate tail for t = 1..T (O(T^2) rows, T <= 16) and
+// collects the K+1 rows of each: out[(k * T + t) * V + v].  Raw logits, no processors.
 extern "C" int wm_forward(wm_handle* h, const int32_t* ids, int32_t n_ids, float* out) {
   if (!h || !ids || !out) return WM_ERR_INVALID;
   if (!h->encoded) return fail(h, WM_ERR_STATE, "wm_encode_* must be called before wm_forward");
@@ -830,13 +830,21 @@ extern "C" int wm_forward(wm_handle* h, const int32_t* ids, int32_t n_ids, float
     CK(cudaMemcpyAsync(h->st, &hs, sizeof hs, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(h->hm.cross_cnt, 0, (size_t)h->cfg.n_heads * sizeof(unsigned int), s));
     CK(cudaMemsetAsync(h->hm.gemm_cnt, 0, (size_t)h->n_sm * sizeof(unsigned int), s));
-    cudaGraphExec_t gA = nullptr, gT = nullptr;
-    int64_t nA = 0, nT = 0;
-    int r;
-    if ((r = get_graph(h, 0, t, &gA, &nA)) != WM_OK) return r;
-    if ((r = get_graph(h, 1, 1, &gT, &nT)) != WM_OK) return r;
-    CK(cudaGraphLaunch(gA, s));
-    CK(cudaGraphLaunch(gT, s));
+    if (h->decode_mode == 2) {
+      // ring kernel (any decode grid): one speculative iteration = sweep A over the prefix, the candidate tail (whose
+      // K+1 logit rows are what we want) and a verify pass whose results are simply not read
+      CK(cudaMemsetAsync(h->bar, 0, 8 * sizeof(unsigned int), s));
+      CK(dec_launch_iteration_ring(h->dm, h->hi, false, s));
+    } else {
+      if (!simple_modes_fit(h)) return fail(h, WM_ERR_UNSUPPORTED, "wm_forward: this decode grid needs the ring kernel (decode_mode 2)");
+      cudaGraphExec_t gA = nullptr, gT = nullptr;
+      int64_t nA = 0, nT = 0;
+      int r;
+      if ((r = get_graph(h, 0, t, &gA, &nA)) != WM_OK) return r;
+      if ((r = get_graph(h, 1, 1, &gT, &nT)) != WM_OK) return r;
+      CK(cudaGraphLaunch(gA, s));
+      CK(cudaGraphLaunch(gT, s));
+    }
     for (int k = 0; k <= K; ++k)
       CK(cudaMemcpyAsync(out + ((size_t)k * n_ids + (t - 1)) * V, h->hm.logits_a + (size_t)k * V, V * sizeof(float),
                          cudaMemcpyDeviceToHost, s));
