@@ -109,7 +109,8 @@ int wm_encode_mel(wm_handle* h, const float* mel);
 int wm_encode_mel_device(wm_handle* h, const float* mel_dev, void* producer_stream);
 
 /* ---- the speculative decode loop (model.py:404-835 + medusa_utils.py:424-671) ---------- */
-/* prompt: decoder_input_ids.  out_ids receives the FULL sequence (prompt + generated, after
+/* prompt: decoder_input_ids, 1 <= n_prompt < max_length - K - 2 (beyond 16 tokens the leading ones are cached by prefill
+ * launches of 16-token chunks).  out_ids receives the FULL sequence (prompt + generated, after
  * the post-EOS fill of model.py:798-810); capacity must be >= max_length + medusa_num_heads + 2.
  * accept_lens (capacity >= max_length, may be NULL) receives the per-iteration accept length. */
 int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt, const wm_gen_params* gp,

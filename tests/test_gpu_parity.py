@@ -508,3 +508,33 @@ def test_tree_limits_are_reported():
     cfg.medusa_choices = [1, 6, 5, 4, 3]            # the example of the reference's docstring: 511 nodes
     with pytest.raises(NotImplementedError):
         WhisperMedusaModel(cfg, synthetic_state_dict(cfg, seed=0)).to("cuda:0")
+
+
+@pytest.mark.parametrize("name", ["micro_linear_k4", "micro_block_k10", "tiny_linear_k4"])
+def test_long_decoder_prompt_is_prefilled_in_chunks(name):
+    """decoder_input_ids longer than the 16 rows of a stage tile (previous-text conditioning): the leading tokens are cached
+    by prefill launches (sweep A over 16-token chunks).  Tokens / accept lengths against the oracle decoding from the
+    engine's encoder states, in the three execution modes; prompt lengths around the chunk boundaries."""
+    g, cfg, seed, stream, kw = _load(name)
+    model, sd = _model(name)
+    pcm = synthetic_audio(float(g["audio_seconds"]), stream_id=stream)
+    w = W.RefWeights(sd)
+    rng = np.random.default_rng(5)
+    base = M.init_tokens(cfg, kw["language"])
+    for n_extra, modes in ((13, ("persistent",)), (14, ("persistent", "graph", "persistent_simple")), (45, ("persistent", "graph"))):
+        prompt = [int(t) for t in rng.integers(20, 400, size=n_extra)] + base      # 15 / 16 / 17 ... / 47+ tokens
+        kw2 = dict(kw, max_length=min(int(kw["max_length"]) + n_extra, 200), decoder_input_ids=torch.tensor([prompt]))
+        want = None
+        for mode in modes:
+            model.set_decode_mode(mode)
+            out = model.generate_from_pcm(pcm, **kw2)[0].tolist()
+            tr = model.last_trace
+            if want is None:
+                enc = model.encoder_output()
+                gp = M.gen_params(cfg, prompt, kw["exponential_decay_length_penalty"], kw2["max_length"],
+                                  temperature=kw["medusa_temperature"])
+                ref = M.medusa_greedy_search(w, cfg, enc, prompt, gp, "engine")
+                want = (ref.sequences, ref.accept_lengths)
+            assert tr.sequences == want[0] and tr.accept_lengths == want[1], (n_extra, mode)
+            assert tr.sequences[: len(prompt)] == prompt and out == M.strip_output(want[0], len(prompt), gp)
+    model.set_decode_mode("persistent")

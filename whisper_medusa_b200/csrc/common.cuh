@@ -204,6 +204,7 @@ struct DecState {
   int begin_index;
   int accept_last;
   int need_a;       // 1 => the newest token is not cached yet: run sweep A before the tail
+  int prefill;      // 1 => this launch only runs sweep A over ids[kv_len .. L) (a 16-token chunk of a long prompt) and stops
   float temperature, post_thr, post_alpha;
   int tree_attn;    // tree mode: 1 = rows attend to their ancestors only (true tree attention), 0 = reference behaviour
   int keep_n;       // tree mode: K/V rows of the verify pass that survive (kept at rows L .. L+keep_n-1) ...

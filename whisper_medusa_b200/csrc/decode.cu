@@ -1427,8 +1427,10 @@ dec_iteration_kernel(const DecModel* __restrict__ m) {
     grid_barrier(bar, epoch, ncta);
   };
   if (need_a) seq_sweep(m->n_layers, m->has_block, MODE_A, run);
-  seq_tail(m->n_layers, m->has_block, run);
-  seq_verify(m->n_layers, m->has_block, run);
+  if (!st->prefill) {   // (prefill: a 16-token chunk of a long prompt -- sweep A only)
+    seq_tail(m->n_layers, m->has_block, run);
+    seq_verify(m->n_layers, m->has_block, run);
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) m->bar[2] = epoch;
 }
 

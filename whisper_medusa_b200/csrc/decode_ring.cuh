@@ -631,7 +631,7 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
   if (warp == WM_DEC_THREADS / 32) {
     // ===== producer warp =====
     const int* off = m->chunk_off + cta * 4;
-    ring_producer<D>(smem, full, empty, m->chunk_tab, need_a ? off[0] : off[1], off[3]);
+    ring_producer<D>(smem, full, empty, m->chunk_tab, need_a ? off[0] : off[1], st->prefill ? off[1] : off[3]);
     return;
   }
 
@@ -642,7 +642,7 @@ dec_iteration_ring_kernel(const DecModel* __restrict__ gm) {
   rs.slot = 0; rs.par = 0u; rs.xpar = 0u; rs.ppar = 0u;
 
   const int ip_first = need_a ? m->prog_off[0] : m->prog_off[1];
-  const int ip_last = m->prog_off[3];
+  const int ip_last = st->prefill ? m->prog_off[1] : m->prog_off[3];   // prefill: sweep A only (a chunk of a long prompt)
   const CtaStage* tab = m->stage_tab + cta;   // record of instruction ip: tab[ip * ncta]
   if (warp == 0)
     reinterpret_cast<uint32_t*>(&s_desc[ip_first & 1])[lane] = reinterpret_cast<const uint32_t*>(tab + (size_t)ip_first * ncta)[lane];

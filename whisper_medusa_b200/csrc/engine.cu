@@ -89,6 +89,8 @@ struct wm_handle {
   int last_pen_start = -2, last_pen_prompt = -1;
 };
 
+static_assert(offsetof(DecState, tree_attn) == 60, "the 16 header words of DecState (L .. tree_attn) are patched as one 64-byte copy");
+
 #define CK(call)                                                                                   \
   do {                                                                                             \
     cudaError_t _e = (call);                                                                       \
@@ -703,7 +705,7 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
   if (!h || !prompt || !gp || !out_ids || !n_out) return WM_ERR_INVALID;
   if (!h->encoded) return fail(h, WM_ERR_STATE, "wm_encode_* must be called before wm_generate");
   const int K = h->cfg.medusa_num_heads;
-  if (n_prompt < 1 || n_prompt > WM_MAX_T) return fail(h, WM_ERR_INVALID, "prompt length must be in [1, 16]");
+  if (n_prompt < 1 || n_prompt + K + 2 > gp->max_length) return fail(h, WM_ERR_INVALID, "prompt length must be in [1, max_length - K - 2)");
   if (gp->max_length > h->cfg.max_target_positions) return fail(h, WM_ERR_INVALID, "max_length exceeds max_target_positions");
   if (gp->temperature < 0.f) return fail(h, WM_ERR_INVALID, "temperature must be >= 0");
   for (int i = 0; i < n_prompt; ++i)
@@ -742,11 +744,42 @@ extern "C" int wm_generate(wm_handle* h, const int32_t* prompt, int32_t n_prompt
     CK(cudaMemsetAsync(h->hm.cross_cnt, 0, (size_t)h->cfg.n_heads * sizeof(unsigned int), s));
     CK(cudaMemsetAsync(h->hm.gemm_cnt, 0, (size_t)h->n_sm * sizeof(unsigned int), s));
   }
+  // Long prompts (decoder_input_ids beyond the 16 rows of a stage tile): the leading tokens are cached by prefill
+  // launches -- sweep A over 16-token chunks, no candidates / verify -- before the loop proper starts on the rest.
+  int n_tail = n_prompt;     // rows of the first real iteration's sweep A
+  {
+    int pos = 0;
+    while (n_prompt - pos > WM_MAX_T) {
+      DecState& hs = *h->h_init;
+      hs.L = pos + WM_MAX_T; hs.kv_len = pos; hs.need_a = 1; hs.prefill = 1;
+      CK(cudaMemcpyAsync(h->st, &hs, 64, cudaMemcpyHostToDevice, s));   // the 16 header words (L .. tree_attn)
+      if (h->decode_mode == 0) {
+        cudaGraphExec_t g = nullptr; int64_t nl = 0; int r;
+        if ((r = get_graph(h, 0, WM_MAX_T, &g, &nl)) != WM_OK) return r;
+        CK(cudaGraphLaunch(g, s));
+        h->launches[2] += nl;
+      } else if (h->decode_mode == 1) {
+        CK(dec_launch_iteration(h->dm, h->hi, s));
+        h->launches[2] += 1;
+      } else {
+        CK(dec_launch_iteration_ring(h->dm, h->hi, false, s));
+        h->launches[2] += 1;
+      }
+      CK(cudaStreamSynchronize(s));   // the pinned header is rewritten for the next chunk
+      pos += WM_MAX_T;
+    }
+    if (pos > 0) {
+      DecState& hs = *h->h_init;
+      hs.L = n_prompt; hs.kv_len = pos; hs.need_a = 1; hs.prefill = 0;
+      CK(cudaMemcpyAsync(h->st, &hs, 64, cudaMemcpyHostToDevice, s));
+      n_tail = n_prompt - pos;
+    }
+  }
   cudaGraphExec_t gA1 = nullptr, gAp = nullptr, gT = nullptr, gB = nullptr;
   int64_t nA1 = 0, nAp = 0, nT = 0, nB = 0;
   if (h->decode_mode == 0) {
     int r;
-    if ((r = get_graph(h, 0, n_prompt, &gAp, &nAp)) != WM_OK) return r;
+    if ((r = get_graph(h, 0, n_tail, &gAp, &nAp)) != WM_OK) return r;
     if ((r = get_graph(h, 0, 1, &gA1, &nA1)) != WM_OK) return r;
     if ((r = get_graph(h, 1, 1, &gT, &nT)) != WM_OK) return r;
     if ((r = get_graph(h, 2, h->hm.n_tree, &gB, &nB)) != WM_OK) return r;

@@ -399,7 +399,8 @@ class WhisperMedusaModel:
             # _multi_heads_generate has no sampling branch (model.py:1130-1156)
             raise NotImplementedError("sampling (temperature > 0 / do_sample) is not supported with medusa: greedy search only")
         known = {"exponential_decay_length_penalty", "max_length", "max_new_tokens", "max_iters", "medusa_temperature",
-                 "posterior_threshold", "posterior_alpha", "num_beams", "do_sample", "use_cache", "tree_attention"}
+                 "posterior_threshold", "posterior_alpha", "num_beams", "do_sample", "use_cache", "tree_attention",
+                 "decoder_input_ids"}
         unknown = sorted(set(kwargs) - known)
         if unknown:
             raise NotImplementedError(f"generate() options not implemented by the B200 engine: {unknown}")
@@ -424,7 +425,13 @@ class WhisperMedusaModel:
         cur = (tuple(g.suppress_tokens or []), tuple(g.begin_suppress_tokens or []))
         if cur != getattr(self, "_pushed", None):
             self._push_suppress()
-        prompt = self._init_tokens(language, task)
+        explicit = kwargs.pop("decoder_input_ids", None)
+        if explicit is not None:
+            # an explicit decoder prompt (HF generate(decoder_input_ids=...)); any length up to max_length - K - 2: tokens
+            # beyond the 16 rows of a stage tile are cached by prefill launches
+            prompt = [int(t) for t in torch.as_tensor(explicit).reshape(-1).tolist()]
+        else:
+            prompt = self._init_tokens(language, task)
         # generate() always runs the loop with temperature 1.0 => typical acceptance (model.py:1878-1881);
         # `medusa_temperature=0` selects the exact-match branch reachable through _medusa_greedy_search.
         t = kwargs.pop("medusa_temperature", 1.0)
