@@ -402,6 +402,9 @@ def main():
                      "tokens_per_s_e2e": sM["tokens"] / grp.last_wall_s, "tokens_per_s_decode_phase": sM["tokens"] / dec_s,
                      "ms_per_iteration_per_stream": sM["ms_per_iteration"], "achieved_gbs": sM["bytes_eng"] / dec_s / 1e9,
                      "frac": sM["bytes_eng"] / dec_s / 1e9 / peak, "vs_batch1_decode": (sM["tokens"] / dec_s) / sm["tokens_per_s"],
+                     # steady state (all S engines decoding): S iterations every ms_per_iteration_per_stream
+                     "steady_state_iteration_rate_vs_batch1": args.streams * sm["ms_per_iteration"] / sM["ms_per_iteration"],
+                     "steady_state_frac": args.streams * (sM["bytes_eng"] / max(1, sM["iterations"])) / (sM["ms_per_iteration"] / 1e3) / 1e9 / peak,
                      "validated": "every stream == its batch-1 tokens", "wall_s": grp.last_wall_s, "encoder_s": enc_s}
             grp.close()
         except SystemExit:
