@@ -135,7 +135,15 @@ __host__ __device__ __forceinline__ GemmWork gemm_work(int N, int K, int d, int 
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
 __host__ __device__ constexpr size_t round128(size_t a) { return (a + 127) / 128 * 128; }
-__host__ __device__ constexpr int ring_nks(int d) { return (d % 256 == 0) ? 8 : (d % 128 == 0) ? 4 : (d % 64 == 0) ? 2 : 1; }
+#ifndef WM_RING_NKS_MAX
+#define WM_RING_NKS_MAX 4   /* A/B round 2 (large-v2, ms per iteration): 8 MMA warps 1.887, 5: 1.900, 4: 1.859, 2: 2.059 */
+#endif
+__host__ __device__ constexpr int ring_nks(int d) {
+#ifdef WM_RING_NKS_FORCE
+  if (d % (WM_RING_NKS_FORCE * 32) == 0) return WM_RING_NKS_FORCE;
+#endif
+  return (d % 256 == 0 && WM_RING_NKS_MAX >= 8) ? 8 : (d % 128 == 0 && WM_RING_NKS_MAX >= 4) ? 4 : (d % 64 == 0) ? 2 : 1;
+}
 
 #define WM_XS_PADB 16   // bytes of X-row padding: stride = 16 (mod 128) => conflict-free LDS.128 / STS.128
 
