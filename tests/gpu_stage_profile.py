@@ -21,7 +21,7 @@ from whisper_medusa_b200 import WhisperMedusaModel, _lib  # noqa: E402
 from whisper_medusa_b200.synthetic import preset_config, synthetic_audio, synthetic_state_dict  # noqa: E402
 
 STAGES = ["EMBED", "QKV", "SELF_ATTN", "OPROJ", "CROSS_Q", "CROSS_ATTN", "CROSS_O", "FC1", "FC2", "FINAL_LN",
-          "COPY_HIDDEN", "TAIL_SEED", "HEADS", "VOCAB", "SELECT1", "SELECT2", "SELECT_FIN", "ACCEPT"]
+          "COPY_HIDDEN", "TAIL_SEED", "HEADS", "VOCAB", "SELECT1", "SELECT2", "SELECT_FIN", "ACCEPT", "KV_COMPACT"]
 MODES = ["A", "B", "TAIL"]
 
 
