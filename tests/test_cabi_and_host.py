@@ -237,3 +237,22 @@ def test_language_tables_match_the_installed_transformers():
     lang = WHISPER_PRESETS["openai/whisper-large-v2"]["lang_to_id"]
     assert lang["<|en|>"] == 50259 and lang["<|su|>"] == 50357 and len(lang) == 99
     assert language_token("English") == "<|en|>" and language_token("fr") == "<|fr|>"
+
+
+def test_preset_suppress_lists_have_the_public_shape():
+    """The suppress-token lists of the built-in presets are reproduced from the public openai/whisper generation configs
+    (no hub access here to diff them; a checkpoint's own generation_config.json takes precedence): at least their shape is
+    pinned -- 88 ids for the multilingual models, 90 for the English-only ones, strictly increasing, inside the vocabulary,
+    containing the special-token block (sot ... notimestamps excluded, translate / transcribe / startoflm / startofprev /
+    nospeech included) and never the EOS token."""
+    from whisper_medusa_b200.config import WHISPER_PRESETS
+
+    for name, n in (("openai/whisper-large-v2", 88), ("openai/whisper-tiny.en", 90)):
+        p = WHISPER_PRESETS[name]
+        s = p["suppress_tokens"]
+        assert len(s) == n and s == sorted(set(s)) and 0 < s[0] and s[-1] < p["vocab_size"]
+        assert p["eos_token_id"] not in s and p["no_timestamps_token_id"] not in s
+        assert p["decoder_start_token_id"] in s            # <|startoftranscript|> may not be re-emitted
+        assert p["begin_suppress_tokens"] == [220, p["eos_token_id"]]
+    big = WHISPER_PRESETS["openai/whisper-large-v2"]
+    assert {big["task_to_id"]["translate"], big["task_to_id"]["transcribe"]} <= set(big["suppress_tokens"])
