@@ -66,6 +66,20 @@ def _load_state_dict(path: str) -> Dict[str, torch.Tensor]:
     return sd
 
 
+class ForwardOutput:
+    """What ``forward`` returns: the fields of the reference's ``Seq2SeqLMOutput`` that an inference engine can fill
+    (reference ``model.py:1335-1347``)."""
+
+    def __init__(self, logits: torch.Tensor):
+        self.logits = logits     # [K+1, 1, T, V] stacked head logits (``[1, 1, T, V]`` with disable_medusa)
+        self.loss = None
+
+    def __getitem__(self, i):    # outputs[0] / outputs["logits"] as HF ModelOutput allows
+        if i in (0, "logits"):
+            return self.logits
+        raise KeyError(i)
+
+
 class GenerateTrace:
     """Per-call measurements (the reference collects ``accept_length_list`` but drops it,
     ``model.py:633,705``)."""
@@ -260,13 +274,13 @@ class WhisperMedusaModel:
         self._pushed = (tuple(sup), tuple(beg))
 
     # ------------------------------------------------------------------ generate
-    def _init_tokens(self, language: Optional[str], task: Optional[str]) -> List[int]:
+    def _init_tokens(self, language: Optional[str], task: Optional[str], g=None) -> List[int]:
         """Prompt ids for the supported cases of HF ``generation_whisper.py:1455-1608``."""
-        g = self.generation_config
+        g = g if g is not None else self.generation_config
         toks = [int(g.decoder_start_token_id)]
         if g.is_multilingual:
             if language is None:
-                lang_id = self._detect_language()
+                lang_id = self._detect_language(g)
             else:
                 from .config import language_token
 
@@ -281,10 +295,10 @@ class WhisperMedusaModel:
         toks.append(int(g.no_timestamps_token_id))
         return toks
 
-    def _detect_language(self) -> int:
+    def _detect_language(self, g=None) -> int:
         """HF ``generation_whisper.py:1559-1566`` / ``detect_language``: one decoder step on ``<|startoftranscript|>``;
         the language token with the largest base logit wins (all non-language ids masked)."""
-        g = self.generation_config
+        g = g if g is not None else self.generation_config
         lang_ids = sorted(int(v) for v in g.lang_to_id.values())
         if not lang_ids:
             raise ValueError("generation_config.lang_to_id is empty: cannot detect the language")
@@ -431,7 +445,7 @@ class WhisperMedusaModel:
             # beyond the 16 rows of a stage tile are cached by prefill launches
             prompt = [int(t) for t in torch.as_tensor(explicit).reshape(-1).tolist()]
         else:
-            prompt = self._init_tokens(language, task)
+            prompt = self._init_tokens(language, task, g)
         # generate() always runs the loop with temperature 1.0 => typical acceptance (model.py:1878-1881);
         # `medusa_temperature=0` selects the exact-match branch reachable through _medusa_greedy_search.
         t = kwargs.pop("medusa_temperature", 1.0)
@@ -484,13 +498,7 @@ class WhisperMedusaModel:
                lib.wm_forward(self._handle, C.cast(ids.data_ptr(), C.POINTER(C.c_int32)), n,
                               C.cast(out.data_ptr(), C.POINTER(C.c_float))), "wm_forward")
 
-        class _Out:
-            pass
-
-        o = _Out()
-        o.logits = (out[:1] if disable_medusa else out).to(self._device)
-        o.loss = None
-        return o
+        return ForwardOutput((out[:1] if disable_medusa else out).to(self._device))
 
     __call__ = forward
 
