@@ -338,6 +338,12 @@ __device__ __noinline__ void stage_gemm(const GemmDesc& g, int cta, int ncta, un
 // Row t sees keys 0 .. base + t.  K/V rows come straight from L2 (the cache is small and hot).
 // -----------------------------------------------------------------------------------------
 #define WM_SA_MAXR 4
+#ifndef WM_SA_PV_UNROLL
+#define WM_SA_PV_UNROLL 4   // independent K/V row loads in flight per thread in the P V loop
+#endif
+#define WM_PRAGMA_(x) _Pragma(#x)
+#define WM_PRAGMA(x) WM_PRAGMA_(x)
+#define WM_UNROLL(n) WM_PRAGMA(unroll n)
 __host__ __device__ constexpr size_t self_attn_smem_bytes() {
   return (size_t)(WM_SA_MAXR * 64 + WM_SA_MAXR * WM_MAX_POS + 2 * WM_SA_MAXR + (WM_DEC_THREADS / 8) * 64) * sizeof(float);
 }
@@ -420,7 +426,7 @@ __device__ __forceinline__ void stage_self_attn(const DecModel* m, int mode, int
       if (r < rg) {
         const int nk = g.base + t0 + r + 1;
         const float* p = s_p + r * WM_MAX_POS;
-#pragma unroll 4
+        WM_UNROLL(WM_SA_PV_UNROLL)
         for (int jj = kg; jj < nk; jj += KG) {
           const uint4 vv = ldcg_u4(L.self_v + (size_t)jj * d + h * 64 + dg * 8);
           const __half2* v2 = reinterpret_cast<const __half2*>(&vv);

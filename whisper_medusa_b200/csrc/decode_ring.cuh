@@ -293,7 +293,9 @@ __device__ __forceinline__ void stage_gemm_ring(RingState& rs, unsigned char* sm
                                                 int Tpass, int base, unsigned long long* pr) {
   using G = RingGeom<D>;
   __shared__ int s_last;
+#if WM_LN_MODE == 0
   __shared__ float2 s_stat[WM_MAX_T];
+#endif
   const int n_rows = sd->n_rows;
   unsigned char* const xb = smem + G::SCRATCH_OFF;
   float* const partial = reinterpret_cast<float*>(smem + G::PARTIAL_OFF);
