@@ -1,10 +1,12 @@
 // Encoder-side dense GEMM on the 5th-generation tensor cores (sm_100a):
 //   C[M,N] = A[M,K] * W[N,K]^T   fp16 operands (both K-major), fp32 accumulation in TMEM.
 //
-// Structure (one 128x128 -- or 128x64 for narrow outputs -- tile per CTA, K swept in 64-column blocks; two CTAs per
-// SM, so one tile's epilogue overlaps the other's main loop):
+// Structure (one 128x128 tile per CTA, K swept in 64-column blocks; 3-stage ring and two CTAs per SM, so one tile's
+// epilogue overlaps the other's main loop -- or, for outputs too narrow to fill the SMs twice, a 6-stage ring and one
+// CTA per SM.  These GEMMs are bound by the L2 -> SM operand traffic ((BM + BN) * K * 2 bytes per tile), not by the
+// tensor pipe: the tile shape is chosen to move the fewest bytes):
 //   warp 0  : TMA producer   -- cp.async.bulk.tensor.2d (SWIZZLE_128B) of the A and W tiles into a
-//                               3-stage shared-memory ring, completion on `full` mbarriers
+//                               shared-memory ring, completion on `full` mbarriers
 //   warp 1  : MMA issuer     -- one elected thread issues tcgen05.mma.cta_group::1.kind::f16
 //                               (M=128, N=128, K=16) x4 per stage, accumulator = 128 TMEM columns;
 //                               tcgen05.commit releases the stage (`empty`) / signals the epilogue
@@ -28,7 +30,9 @@ namespace wm {
 #define TC_BM 128
 #define TC_BN 128
 #define TC_BK 64
-#define TC_STAGES 3
+#ifndef WM_TC_NARROW_BN
+#define WM_TC_NARROW_BN 128   /* tile width for outputs of <= 1536 columns (64: twice the tiles, 3 stages, 2 CTAs / SM) */
+#endif
 #define TC_THREADS 320
 #define TC_TMEM_COLS 128
 #define TC_STAGE_BYTES ((TC_BM + TC_BN) * TC_BK * 2)   /* layout of a stage for every tile width: A at 0, W at 16 KB */
@@ -41,14 +45,15 @@ struct TcArgs {
   float* out32; int ldo32;
   const float* pos;
   __half* vt; int vt_col0, vt_ld;   // columns >= vt_col0 are ALSO written transposed: vt[col - vt_col0][row] (null: off)
+  __half* ck; __half* cv; int kv_spad;   // non-null: the output [pos][k | v] goes to the decode layout [head][kv_spad][72]
 };
 
-template <int EPI, int BN>
+template <int EPI, int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // stage s: A tile [128 rows][64 halfs] at s*32K, W tile at s*32K + 16K (both 1024-B aligned, SW128)
-  __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tmem_full;
+  __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], s_tmem_full;
   __shared__ uint32_t s_tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
@@ -58,7 +63,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       tc_mbar_init(tc_smem_u32(&s_full[s]), 1);
       tc_mbar_init(tc_smem_u32(&s_empty[s]), 1);
     }
@@ -80,8 +85,8 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // ===== TMA producer =====
     if (lane == 0) {
       for (int kt = 0; kt < KT; ++kt) {
-        const int s = kt % TC_STAGES;
-        const uint32_t ph = (kt / TC_STAGES) & 1;
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
         tc_mbar_wait(tc_smem_u32(&s_empty[s]), ph ^ 1);
         const uint32_t full = tc_smem_u32(&s_full[s]);
         tc_mbar_expect_tx(full, (TC_BM + BN) * TC_BK * 2);
@@ -94,8 +99,8 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (lane == 0) {
       const uint32_t idesc = tc_instr_desc(BN);
       for (int kt = 0; kt < KT; ++kt) {
-        const int s = kt % TC_STAGES;
-        const uint32_t ph = (kt / TC_STAGES) & 1;
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
         tc_mbar_wait(tc_smem_u32(&s_full[s]), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t adesc = tc_smem_desc(smem_base + s * TC_STAGE_BYTES);
@@ -124,6 +129,13 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       if ((EPI == ENC_EPI_BIAS_F16 || EPI == ENC_EPI_BIAS_GELU_F16) && !row_ok) continue;   // (fp32 epilogues: warp-cooperative)
       if (EPI == ENC_EPI_BIAS_F16 || EPI == ENC_EPI_BIAS_GELU_F16) {
         __half* dst = a.out16 + (size_t)row * a.ldo16 + col0;
+        if (EPI == ENC_EPI_BIAS_F16 && a.ck != nullptr) {
+          // cross-attention K/V straight into the layout the decode kernels read: [head][position][64 dims + 8 pad]
+          // (pad halfs and positions >= M stay zero from the allocation); 64 contiguous bytes per thread as above
+          const int dm = a.N >> 1;
+          const int cc = col0 >= dm ? col0 - dm : col0;
+          dst = (col0 >= dm ? a.cv : a.ck) + ((size_t)(cc >> 6) * a.kv_spad + row) * 72 + (cc & 63);
+        }
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
           uint32_t pk[4];
@@ -223,20 +235,20 @@ static bool make_map(CUtensorMap* map, const __half* base, uint64_t rows, uint64
   return r == CUDA_SUCCESS;
 }
 
-static const size_t kTcSmem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
+static constexpr size_t tc_smem(int stages) { return (size_t)stages * TC_STAGE_BYTES + 1024; }
 
 cudaError_t enc_gemm_tc_configure() {
   cudaError_t e;
-#define WM_SET(EPI)                                                                                              \
-  e = cudaFuncSetAttribute(enc_gemm_tc_kernel<EPI, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem); \
-  if (e != cudaSuccess) return e;                                                                                 \
-  e = cudaFuncSetAttribute(enc_gemm_tc_kernel<EPI, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);  \
+#define WM_SET1(EPI, BN, ST)                                                                                             \
+  e = cudaFuncSetAttribute(enc_gemm_tc_kernel<EPI, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(ST)); \
   if (e != cudaSuccess) return e;
+#define WM_SET(EPI) WM_SET1(EPI, 128, 3) WM_SET1(EPI, 128, 6) WM_SET1(EPI, 64, 3)
   WM_SET(ENC_EPI_BIAS_F16)
   WM_SET(ENC_EPI_BIAS_GELU_F16)
   WM_SET(ENC_EPI_BIAS_RES_F32)
   WM_SET(ENC_EPI_BIAS_GELU_POS_F32)
 #undef WM_SET
+#undef WM_SET1
   return get_encode_fn() ? cudaSuccess : cudaErrorNotSupported;
 }
 
@@ -257,33 +269,34 @@ cudaError_t enc_gemm_tc(const EncGemmArgs& g, int a_rows, cudaStream_t s, int64_
     return true;
   };
   CUtensorMap ma, mw;
-  const int bn = (g.N <= 1536 && g.N % 64 == 0) ? 64 : TC_BN;   // narrow outputs: twice the tiles, all SMs busy
+  // narrow outputs (N <= 1536: fewer than one 128 x 128 tile per SM): one CTA per SM with a deep ring -- 25 % fewer
+  // operand bytes through L2 than 128 x 64 tiles, which is what bounds these GEMMs
+  const bool narrow = g.N <= 1536;
+  const int bn = (narrow && WM_TC_NARROW_BN == 64 && g.N % 64 == 0) ? 64 : TC_BN;
+  const int stages = (narrow && bn == TC_BN) ? 6 : 3;
   if (!get(g.A, (uint64_t)a_rows, (uint64_t)g.K, (uint64_t)g.lda, TC_BM, &ma)) return cudaErrorInvalidValue;
   if (!get(g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.K, (uint32_t)bn, &mw)) return cudaErrorInvalidValue;
   TcArgs a;
   a.M = g.M; a.N = g.N; a.K = g.K; a.epi = g.epi; a.bias = g.bias; a.out16 = g.out16; a.ldo16 = g.ldo16;
   a.out32 = g.out32; a.ldo32 = g.ldo32; a.pos = g.pos;
   a.vt = g.vt; a.vt_col0 = g.vt_col0; a.vt_ld = g.vt_ld;
+  a.ck = g.ck; a.cv = g.cv; a.kv_spad = g.kv_spad;
+  if (a.ck != nullptr && (g.epi != ENC_EPI_BIAS_F16 || (g.N >> 1) % 64 != 0)) return cudaErrorInvalidValue;
   dim3 grid(g.N / bn, (g.M + TC_BM - 1) / TC_BM);
+#define WM_LAUNCH(EPI)                                                                                                  \
+  case EPI:                                                                                                             \
+    if (bn == 64) enc_gemm_tc_kernel<EPI, 64, 3><<<grid, TC_THREADS, tc_smem(3), s>>>(ma, mw, a);                       \
+    else if (stages == 6) enc_gemm_tc_kernel<EPI, 128, 6><<<grid, TC_THREADS, tc_smem(6), s>>>(ma, mw, a);              \
+    else enc_gemm_tc_kernel<EPI, 128, 3><<<grid, TC_THREADS, tc_smem(3), s>>>(ma, mw, a);                               \
+    break;
   switch (g.epi) {
-    case ENC_EPI_BIAS_F16:
-      if (bn == 64) enc_gemm_tc_kernel<ENC_EPI_BIAS_F16, 64><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
-      else enc_gemm_tc_kernel<ENC_EPI_BIAS_F16, 128><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
-      break;
-    case ENC_EPI_BIAS_GELU_F16:
-      if (bn == 64) enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_F16, 64><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
-      else enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_F16, 128><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
-      break;
-    case ENC_EPI_BIAS_RES_F32:
-      if (bn == 64) enc_gemm_tc_kernel<ENC_EPI_BIAS_RES_F32, 64><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
-      else enc_gemm_tc_kernel<ENC_EPI_BIAS_RES_F32, 128><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
-      break;
-    case ENC_EPI_BIAS_GELU_POS_F32:
-      if (bn == 64) enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_POS_F32, 64><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
-      else enc_gemm_tc_kernel<ENC_EPI_BIAS_GELU_POS_F32, 128><<<grid, TC_THREADS, kTcSmem, s>>>(ma, mw, a);
-      break;
+    WM_LAUNCH(ENC_EPI_BIAS_F16)
+    WM_LAUNCH(ENC_EPI_BIAS_GELU_F16)
+    WM_LAUNCH(ENC_EPI_BIAS_RES_F32)
+    WM_LAUNCH(ENC_EPI_BIAS_GELU_POS_F32)
     default: return cudaErrorInvalidValue;
   }
+#undef WM_LAUNCH
   if (n_launch) ++*n_launch;
   return cudaGetLastError();
 }

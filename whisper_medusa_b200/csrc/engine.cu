@@ -607,8 +607,14 @@ static int run_encoder(wm_handle* h) {
     memset(&a, 0, sizeof a);
     a.A = h->enc16; a.lda = d; a.W = wptr<__half>(h, p + "ckv_w"); a.bias = wptr<float>(h, p + "ckv_b");
     a.M = S; a.N = 2 * d; a.K = d; a.epi = ENC_EPI_BIAS_F16; a.out16 = h->qkv16; a.ldo16 = 2 * d;   // (scratch: [pos][k | v])
-    CK(gemm_dispatch(h, a, s, nl));
-    CK(dec_relayout_cross_kv(h->qkv16, h->cross_k[i], h->cross_v[i], S, h->S_pad, d, h->cfg.n_heads, s, nl));
+    if (h->enc_gemm_impl == 1 && d % 64 == 0) {
+      // the tcgen05 GEMM's epilogue writes the decode layout itself (pad entries stay zero from the allocation)
+      a.ck = h->cross_k[i]; a.cv = h->cross_v[i]; a.kv_spad = h->S_pad;
+      CK(gemm_dispatch(h, a, s, nl));
+    } else {
+      CK(gemm_dispatch(h, a, s, nl));
+      CK(dec_relayout_cross_kv(h->qkv16, h->cross_k[i], h->cross_v[i], S, h->S_pad, d, h->cfg.n_heads, s, nl));
+    }
   }
   return WM_OK;
 }

@@ -56,6 +56,8 @@ struct EncGemmArgs {
   const float* pos;             // [M, N] added after GELU (conv2)
   __half* vt; int vt_col0, vt_ld;   // tcgen05 GEMM, ENC_EPI_BIAS_F16 only: columns >= vt_col0 also written transposed
                                     // (vt[col - vt_col0][row], row stride vt_ld): V^T for the tcgen05 attention
+  __half* ck; __half* cv; int kv_spad;   // tcgen05 GEMM, ENC_EPI_BIAS_F16 only: the output [pos][k | v] (N = 2 d) goes to the
+                                         // decode layout cross_k / cross_v [head][kv_spad][72] instead of out16
 };
 cudaError_t enc_gemm(const EncGemmArgs& a, cudaStream_t s, int64_t* n_launch);
 cudaError_t enc_gemm_configure();
