@@ -231,6 +231,14 @@ def test_large_v2_tokens_bit_exact_vs_golden(mode):
             lg = model.last_logits(which).numpy()
             assert _rel_err(lg, ref.numpy()) < 1e-3, ab
             assert _rel_err(lg[:, ::97], g[f"logits{ab}0_strided"]) < 5e-3, ab
+        # tcgen05 GEMM tile shapes: at d = 1280 the wide outputs run as 256 x 192 / 256 x 256 / 256 x 128 tiles (two
+        # 128-row accumulators per CTA); option enc_gemm = 2 forces 128-row tiles.  Same operands, same K order per
+        # output element => identical encoder states.
+        model.set_option("enc_gemm", 2)
+        model.generate_from_pcm(pcm, max_iters=1, **kw)
+        enc128 = model.encoder_output()
+        model.set_option("enc_gemm", 1)
+        assert torch.equal(enc128, enc)
 
 
 @pytest.mark.skipif(not os.path.isfile(os.path.join(GOLDEN, "large_block_k10.npz")), reason="fixture missing")

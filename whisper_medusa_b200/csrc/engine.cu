@@ -74,6 +74,7 @@ struct wm_handle {
   int64_t launches_tail = 0, launches_b = 0;
   int decode_mode = 0;
   int enc_gemm_impl = 0;   // 0 = mma.sync kernel, 1 = tcgen05/TMA kernel
+  int enc_gemm_tile = 0;   // tcgen05 kernel: 0 = tile shape picked per GEMM, 1 = 128-row tiles only (option "enc_gemm" = 2)
   int enc_attn_impl = 0;   // 0 = mma.sync flash attention, 1 = tcgen05/TMA/TMEM attention
   bool tc_ok = false, attn_tc_ok = false;
   bool encoded = false;
@@ -554,7 +555,11 @@ extern "C" int wm_set_suppress(wm_handle* h, const int32_t* sup, int32_t n_sup, 
 // frontend + encoder
 // ---------------------------------------------------------------------------------------------
 static cudaError_t gemm_dispatch(wm_handle* h, const EncGemmArgs& a, cudaStream_t s, int64_t* nl) {
-  if (h->enc_gemm_impl == 1) return enc_gemm_tc(a, (int)align_up((size_t)a.M, 128), s, nl);
+  if (h->enc_gemm_impl == 1) {
+    EncGemmArgs b = a;
+    b.tile = h->enc_gemm_tile;
+    return enc_gemm_tc(b, (int)align_up((size_t)a.M, 128), s, nl);
+  }
   return enc_gemm(a, s, nl);
 }
 
@@ -970,8 +975,11 @@ extern "C" int wm_set_option(wm_handle* h, const char* key, int32_t value) {
   }
   if (k == "enc_gemm") {
     if (value == 1 && !h->tc_ok) return fail(h, WM_ERR_UNSUPPORTED, "tcgen05 GEMM unavailable (cuTensorMapEncodeTiled not found)");
-    if (value < 0 || value > 1) return fail(h, WM_ERR_INVALID, "enc_gemm must be 0 (mma.sync) or 1 (tcgen05)");
-    h->enc_gemm_impl = value;
+    if (value < 0 || value > 2)
+      return fail(h, WM_ERR_INVALID, "enc_gemm must be 0 (mma.sync), 1 (tcgen05) or 2 (tcgen05, 128-row tiles only)");
+    if (value >= 1 && !h->tc_ok) return fail(h, WM_ERR_UNSUPPORTED, "tcgen05 GEMM unavailable (cuTensorMapEncodeTiled not found)");
+    h->enc_gemm_impl = value ? 1 : 0;
+    h->enc_gemm_tile = value == 2 ? 1 : 0;
     return WM_OK;
   }
   return fail(h, WM_ERR_INVALID, "unknown option " + k);

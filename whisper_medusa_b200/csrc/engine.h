@@ -58,6 +58,7 @@ struct EncGemmArgs {
                                     // (vt[col - vt_col0][row], row stride vt_ld): V^T for the tcgen05 attention
   __half* ck; __half* cv; int kv_spad;   // tcgen05 GEMM, ENC_EPI_BIAS_F16 only: the output [pos][k | v] (N = 2 d) goes to the
                                          // decode layout cross_k / cross_v [head][kv_spad][72] instead of out16
+  int tile;                     // tcgen05 GEMM: 0 = tile shape picked per GEMM, 1 = 128-row tiles only (cross-check)
 };
 cudaError_t enc_gemm(const EncGemmArgs& a, cudaStream_t s, int64_t* n_launch);
 cudaError_t enc_gemm_configure();
