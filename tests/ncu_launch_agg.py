@@ -1,3 +1,8 @@
+"""Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel name and grid:
+
+    python tests/ncu_launch_agg.py profiles/r2_launches_bench_steps1.csv
+
+Runs on the CPU box."""
 import csv,collections,sys
 rows=list(csv.reader(open(sys.argv[1])))
 hdr=None
