@@ -143,6 +143,12 @@ def test_encoder_gemm_implementations_agree(name):
     for o in outs:
         assert np.abs(o[::50] - g["enc_sample"]).max() < 5e-3
     assert toks[0].tolist() == toks[1].tolist()
+    # plain stream-ordered launches instead of programmatic dependent launch: same bits
+    model.set_option("enc_pdl", 0)
+    model.generate_from_pcm(pcm, **kw)
+    plain = model.encoder_output().numpy()
+    model.set_option("enc_pdl", 1)
+    assert np.array_equal(plain, outs[0])
 
 
 @pytest.mark.parametrize("name", ["micro_linear_k4", "tiny_linear_k4"])
@@ -239,6 +245,17 @@ def test_large_v2_tokens_bit_exact_vs_golden(mode):
         enc128 = model.encoder_output()
         model.set_option("enc_gemm", 1)
         assert torch.equal(enc128, enc)
+        # programmatic dependent launch (default): every encoder kernel may start while its predecessor drains and does
+        # its set-up and first weight loads before the grid-dependency wait; plain stream-ordered launches (enc_pdl = 0)
+        # must give the same bits, run after run
+        model.set_option("enc_pdl", 0)
+        model.generate_from_pcm(pcm, max_iters=1, **kw)
+        enc_plain = model.encoder_output()
+        model.set_option("enc_pdl", 1)
+        assert torch.equal(enc_plain, enc)
+        for _ in range(3):
+            model.generate_from_pcm(pcm, max_iters=1, **kw)
+            assert torch.equal(model.encoder_output(), enc)
 
 
 @pytest.mark.skipif(not os.path.isfile(os.path.join(GOLDEN, "large_block_k10.npz")), reason="fixture missing")

@@ -79,6 +79,10 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem_base;
   const uint32_t tS0 = tmem_base, tD = tmem_base + 128;   // S buffers at columns 0 and 64, D at 128
+  // programmatic dependent launch (tc_common.cuh): everything above overlapped the QKV GEMM's tail; Q, K and V^T are its
+  // outputs
+  tc_grid_dep_launch();
+  tc_grid_dep_wait();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -301,7 +305,7 @@ cudaError_t enc_attention_tc_configure() {
 
 // qkv: [S_pad][3d] fp16 (q | k | v), vt: scratch [d][S_pad] fp16, out: [S_pad][d] fp16
 cudaError_t enc_attention_tc(const __half* qkv, __half* vt, __half* out, int S, int S_pad, int d, int H, bool vt_ready,
-                             cudaStream_t s, int64_t* n_launch) {
+                             cudaStream_t s, int64_t* n_launch, bool pdl) {
   typedef std::tuple<const void*, const void*, int, int> Key;
   struct Maps { CUtensorMap q, k, vt; };
   static thread_local std::map<Key, Maps> cache;
@@ -319,7 +323,9 @@ cudaError_t enc_attention_tc(const __half* qkv, __half* vt, __half* out, int S, 
     if (n_launch) ++*n_launch;
   }
   dim3 grid((S + AT_BQ - 1) / AT_BQ, H);
-  enc_attn_tc_kernel<<<grid, AT_THREADS, kAtSmem, s>>>(it->second.q, it->second.k, it->second.vt, out, S, d);
+  cudaError_t e = tc_launch(enc_attn_tc_kernel, grid, dim3(AT_THREADS), kAtSmem, s, pdl && vt_ready, it->second.q, it->second.k,
+                            it->second.vt, out, S, d);
+  if (e != cudaSuccess) return e;
   if (n_launch) ++*n_launch;
   return cudaGetLastError();
 }

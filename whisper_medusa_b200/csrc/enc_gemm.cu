@@ -8,6 +8,7 @@
 // enc_gemm_tc.cu replaces it on the hot path once validated against it.
 #include "common.cuh"
 #include "engine.h"
+#include "tc_common.cuh"
 
 namespace wm {
 
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(256) enc_layernorm_kernel(const float* __restr
                                                             float* __restrict__ y32, int M, int d) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  tc_grid_dep_launch();                        // (programmatic dependent launch, tc_common.cuh)
+  tc_grid_dep_wait();                          // x is the predecessor's output
   if (row >= M) return;
   const int nv = d >> 7;                       // float4 per lane
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d) + lane;
@@ -205,9 +208,10 @@ __global__ void __launch_bounds__(256) enc_layernorm_kernel(const float* __restr
 }
 
 cudaError_t enc_layernorm(const float* x, const float* g, const float* b, __half* y16, float* y32, int M, int d,
-                          cudaStream_t s, int64_t* n_launch) {
+                          cudaStream_t s, int64_t* n_launch, bool pdl) {
   const int wpb = 8;
-  enc_layernorm_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, s>>>(x, g, b, y16, y32, M, d);
+  cudaError_t e = tc_launch(enc_layernorm_kernel, dim3((M + wpb - 1) / wpb), dim3(wpb * 32), 0, s, pdl, x, g, b, y16, y32, M, d);
+  if (e != cudaSuccess) return e;
   if (n_launch) ++*n_launch;
   return cudaGetLastError();
 }

@@ -101,17 +101,29 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem_base;
+  tc_grid_dep_launch();
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kt = 0; kt < KT; ++kt) {
+      // the weight tiles of the first ring round do not depend on the predecessor kernel: they are requested before the
+      // grid-dependency wait (programmatic dependent launch, tc_common.cuh), the activation tiles after it
+      const int pre = KT < STAGES ? KT : STAGES;
+      for (int kt = 0; kt < pre; ++kt) {
+        const uint32_t full = tc_smem_u32(&s_full[kt]);
+        tc_mbar_expect_tx(full, (MB * TC_BM + BN) * TC_BK * 2);
+        tc_tma_load_2d(smem_base + kt * STAGE_BYTES + A_BYTES, &map_w, kt * TC_BK, n0, full);
+      }
+      tc_grid_dep_wait();
+      for (int kt = 0; kt < pre; ++kt)
+        tc_tma_load_2d(smem_base + kt * STAGE_BYTES, &map_a, kt * TC_BK, m0, tc_smem_u32(&s_full[kt]));   // (one box of 128 MB rows)
+      for (int kt = pre; kt < KT; ++kt) {
         const int s = kt % STAGES;
         const uint32_t ph = (kt / STAGES) & 1;
         tc_mbar_wait(tc_smem_u32(&s_empty[s]), ph ^ 1);
         const uint32_t full = tc_smem_u32(&s_full[s]);
         tc_mbar_expect_tx(full, (MB * TC_BM + BN) * TC_BK * 2);
-        tc_tma_load_2d(smem_base + s * STAGE_BYTES, &map_a, kt * TC_BK, m0, full);   // (one box of 128 MB rows)
+        tc_tma_load_2d(smem_base + s * STAGE_BYTES, &map_a, kt * TC_BK, m0, full);
         tc_tma_load_2d(smem_base + s * STAGE_BYTES + A_BYTES, &map_w, kt * TC_BK, n0, full);
       }
     }
@@ -149,6 +161,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     constexpr int NBLK = MB * (BN / 32) / NEPI_Q;   // 32 x 32 blocks per warp
     constexpr bool F32_OUT = (EPI == ENC_EPI_BIAS_RES_F32 || EPI == ENC_EPI_BIAS_GELU_POS_F32);
     for (int i = (int)threadIdx.x - 64; i < BN; i += NEPI_T) s_bias[i] = a.bias[n0 + i];
+    tc_grid_dep_wait();   // (the epilogue reads and writes activations)
     asm volatile("bar.sync 1, %0;" ::"n"(NEPI_T) : "memory");   // (epilogue warps only) s_bias complete
     tc_mbar_wait(tc_smem_u32(&s_tmem_full), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -354,14 +367,17 @@ cudaError_t enc_gemm_tc(const EncGemmArgs& g, int a_rows, cudaStream_t s, int64_
   if (a.ck != nullptr && (g.epi != ENC_EPI_BIAS_F16 || (g.N >> 1) % 64 != 0)) return cudaErrorInvalidValue;
   dim3 grid(g.N / t.bn, (g.M + t.mb * TC_BM - 1) / (t.mb * TC_BM));
   bool launched = false;
+  cudaError_t le = cudaSuccess;
 #define WM_LAUNCH(EPI, MB, BN, ST)                                                                                       \
   if (!launched && g.epi == EPI && t.mb == MB && t.bn == BN && t.stages == ST) {                                          \
-    enc_gemm_tc_kernel<EPI, MB, BN, ST><<<grid, MB == 1 ? TC_THREADS : TC_THREADS_WIDE, tc_smem(MB, BN, ST), s>>>(ma, mw, a); \
+    le = tc_launch(enc_gemm_tc_kernel<EPI, MB, BN, ST>, grid, dim3(MB == 1 ? TC_THREADS : TC_THREADS_WIDE),               \
+                   tc_smem(MB, BN, ST), s, g.pdl != 0, ma, mw, a);                                                        \
     launched = true;                                                                                                     \
   }
   WM_TC_ALL(WM_LAUNCH)
 #undef WM_LAUNCH
   if (!launched) return cudaErrorInvalidValue;
+  if (le != cudaSuccess) return le;
   if (n_launch) ++*n_launch;
   return cudaGetLastError();
 }

@@ -74,6 +74,7 @@ struct wm_handle {
   int64_t launches_tail = 0, launches_b = 0;
   int decode_mode = 0;
   int enc_gemm_impl = 0;   // 0 = mma.sync kernel, 1 = tcgen05/TMA kernel
+  int enc_pdl = 1;         // encoder kernels launched with programmatic stream serialization (option "enc_pdl" = 0: plain launches)
   int enc_gemm_tile = 0;   // tcgen05 kernel: 0 = tile shape picked per GEMM, 1 = 128-row tiles only (option "enc_gemm" = 2)
   int enc_attn_impl = 0;   // 0 = mma.sync flash attention, 1 = tcgen05/TMA/TMEM attention
   bool tc_ok = false, attn_tc_ok = false;
@@ -558,6 +559,7 @@ static cudaError_t gemm_dispatch(wm_handle* h, const EncGemmArgs& a, cudaStream_
   if (h->enc_gemm_impl == 1) {
     EncGemmArgs b = a;
     b.tile = h->enc_gemm_tile;
+    b.pdl = h->enc_pdl;
     return enc_gemm_tc(b, (int)align_up((size_t)a.M, 128), s, nl);
   }
   return enc_gemm(a, s, nl);
@@ -582,20 +584,20 @@ static int run_encoder(wm_handle* h) {
   CK(gemm_dispatch(h, a, s, nl));
   for (int i = 0; i < c.enc_layers; ++i) {
     std::string p = "enc." + std::to_string(i) + ".";
-    CK(enc_layernorm(h->x32, wptr<float>(h, p + "ln1_g"), wptr<float>(h, p + "ln1_b"), h->ln16, nullptr, S, d, s, nl));
+    CK(enc_layernorm(h->x32, wptr<float>(h, p + "ln1_g"), wptr<float>(h, p + "ln1_b"), h->ln16, nullptr, S, d, s, nl, h->enc_pdl != 0));
     memset(&a, 0, sizeof a);
     a.A = h->ln16; a.lda = d; a.W = wptr<__half>(h, p + "qkv_w"); a.bias = wptr<float>(h, p + "qkv_b");
     a.M = S; a.N = 3 * d; a.K = d; a.epi = ENC_EPI_BIAS_F16; a.out16 = h->qkv16; a.ldo16 = 3 * d;
     const bool vt_fused = (h->enc_attn_impl == 1 && h->enc_gemm_impl == 1);   // the tcgen05 GEMM epilogue writes V^T too
     if (vt_fused) { a.vt = h->vt16; a.vt_col0 = 2 * d; a.vt_ld = h->S_pad; }
     CK(gemm_dispatch(h, a, s, nl));
-    if (h->enc_attn_impl == 1) CK(enc_attention_tc(h->qkv16, h->vt16, h->att16, S, h->S_pad, d, c.n_heads, vt_fused, s, nl));
+    if (h->enc_attn_impl == 1) CK(enc_attention_tc(h->qkv16, h->vt16, h->att16, S, h->S_pad, d, c.n_heads, vt_fused, s, nl, h->enc_pdl != 0));
     else CK(enc_attention(h->qkv16, h->att16, S, d, c.n_heads, s, nl));
     memset(&a, 0, sizeof a);
     a.A = h->att16; a.lda = d; a.W = wptr<__half>(h, p + "o_w"); a.bias = wptr<float>(h, p + "o_b");
     a.M = S; a.N = d; a.K = d; a.epi = ENC_EPI_BIAS_RES_F32; a.out32 = h->x32; a.ldo32 = d;
     CK(gemm_dispatch(h, a, s, nl));
-    CK(enc_layernorm(h->x32, wptr<float>(h, p + "ln2_g"), wptr<float>(h, p + "ln2_b"), h->ln16, nullptr, S, d, s, nl));
+    CK(enc_layernorm(h->x32, wptr<float>(h, p + "ln2_g"), wptr<float>(h, p + "ln2_b"), h->ln16, nullptr, S, d, s, nl, h->enc_pdl != 0));
     memset(&a, 0, sizeof a);
     a.A = h->ln16; a.lda = d; a.W = wptr<__half>(h, p + "fc1_w"); a.bias = wptr<float>(h, p + "fc1_b");
     a.M = S; a.N = f; a.K = d; a.epi = ENC_EPI_BIAS_GELU_F16; a.out16 = h->ffn16; a.ldo16 = f;
@@ -605,7 +607,7 @@ static int run_encoder(wm_handle* h) {
     a.M = S; a.N = d; a.K = f; a.epi = ENC_EPI_BIAS_RES_F32; a.out32 = h->x32; a.ldo32 = d;
     CK(gemm_dispatch(h, a, s, nl));
   }
-  CK(enc_layernorm(h->x32, wptr<float>(h, "enc.lnf_g"), wptr<float>(h, "enc.lnf_b"), h->enc16, h->enc32, S, d, s, nl));
+  CK(enc_layernorm(h->x32, wptr<float>(h, "enc.lnf_g"), wptr<float>(h, "enc.lnf_b"), h->enc16, h->enc32, S, d, s, nl, h->enc_pdl != 0));
   // cross-attention K/V of every decoder layer, re-laid out per head for the decode kernels (cross_k / cross_v)
   for (int i = 0; i < h->n_dec; ++i) {
     std::string p = "dec." + std::to_string(i) + ".";
@@ -971,6 +973,11 @@ extern "C" int wm_set_option(wm_handle* h, const char* key, int32_t value) {
     if (value == 1 && !h->attn_tc_ok) return fail(h, WM_ERR_UNSUPPORTED, "tcgen05 attention unavailable (cuTensorMapEncodeTiled not found)");
     if (value < 0 || value > 1) return fail(h, WM_ERR_INVALID, "enc_attn must be 0 (mma.sync) or 1 (tcgen05)");
     h->enc_attn_impl = value;
+    return WM_OK;
+  }
+  if (k == "enc_pdl") {
+    if (value < 0 || value > 1) return fail(h, WM_ERR_INVALID, "enc_pdl must be 0 or 1");
+    h->enc_pdl = value;
     return WM_OK;
   }
   if (k == "enc_gemm") {

@@ -59,12 +59,14 @@ struct EncGemmArgs {
   __half* ck; __half* cv; int kv_spad;   // tcgen05 GEMM, ENC_EPI_BIAS_F16 only: the output [pos][k | v] (N = 2 d) goes to the
                                          // decode layout cross_k / cross_v [head][kv_spad][72] instead of out16
   int tile;                     // tcgen05 GEMM: 0 = tile shape picked per GEMM, 1 = 128-row tiles only (cross-check)
+  int pdl;                      // tcgen05 GEMM: launch with programmatic stream serialization (tc_common.cuh)
 };
 cudaError_t enc_gemm(const EncGemmArgs& a, cudaStream_t s, int64_t* n_launch);
 cudaError_t enc_gemm_configure();
 // LayerNorm rows of fp32 x [M, d] -> fp16 y [M, d] (and optional fp32 copy)
+// (pdl: launched with programmatic stream serialization, see tc_common.cuh)
 cudaError_t enc_layernorm(const float* x, const float* g, const float* b, __half* y16, float* y32, int M, int d,
-                          cudaStream_t s, int64_t* n_launch);
+                          cudaStream_t s, int64_t* n_launch, bool pdl = false);
 
 // ---- enc_gemm_tc.cu (tcgen05 + TMA + TMEM) ----
 cudaError_t enc_gemm_tc(const EncGemmArgs& a, int a_rows, cudaStream_t s, int64_t* n_launch);
@@ -78,7 +80,7 @@ cudaError_t enc_attention(const __half* qkv, __half* out, int S, int d, int H, c
 // qkv as above; vt: scratch fp16 [d][S_pad] (V transposed, written here); out: fp16 [S_pad, d]
 // vt_ready: the QKV GEMM already wrote V^T (EncGemmArgs::vt); otherwise a transpose kernel runs first
 cudaError_t enc_attention_tc(const __half* qkv, __half* vt, __half* out, int S, int S_pad, int d, int H, bool vt_ready,
-                             cudaStream_t s, int64_t* n_launch);
+                             cudaStream_t s, int64_t* n_launch, bool pdl = false);
 cudaError_t enc_attention_tc_configure();
 
 }  // namespace wm

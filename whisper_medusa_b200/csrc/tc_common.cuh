@@ -1,7 +1,10 @@
 // tcgen05 / TMA / mbarrier helpers shared by the encoder kernels (sm_100a).
 #pragma once
 #include <cuda.h>
+#include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <utility>
 
 namespace wm {
 
@@ -76,5 +79,26 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Programmatic dependent launch (the encoder's kernels form one dependent chain on one stream): a kernel launched with
+// pdl = true may start while its predecessor is still running; it must not touch anything the predecessor writes (or
+// write anything the predecessor reads) before tc_grid_dep_wait(), which returns once the predecessor grid has completed
+// and its memory is visible.  What runs before the wait -- barrier / TMEM set-up, tensor-map fetches, the first WEIGHT
+// tiles, bias rows -- overlaps the predecessor's epilogue and drain.  tc_grid_dep_launch() lets the successor be
+// scheduled as soon as every CTA of this grid has started (the successor's CTAs only take SM resources that are free).
+// Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void tc_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void tc_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t tc_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 }  // namespace wm
