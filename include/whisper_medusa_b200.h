@@ -142,8 +142,10 @@ int wm_set_decode_mode(wm_handle* h, int32_t mode);
 void* wm_weights_device_ptr(wm_handle* h);
 /* Engine options: "decode_ctas" = CTAs of the decode grid (default: every SM; S handles with n_sm / S each decode S
  * streams concurrently -- SURVEY 8(f) rank 3, the reference is batch 1 at model.py:1451); "decode_mode" (as above); "enc_gemm" 1 = tcgen05/TMA/TMEM encoder GEMM (default),
- * 0 = mma.sync encoder GEMM (cross-check); "enc_attn" 1 = tcgen05/TMA/TMEM encoder attention (default), 0 = mma.sync
- * flash attention (cross-check); "profile" 1 = record the stage timeline below. */
+ * 0 = mma.sync encoder GEMM (cross-check), 2 = tcgen05 with 128-row tiles only (cross-check of the per-GEMM tile
+ * shapes); "enc_attn" 1 = tcgen05/TMA/TMEM encoder attention (default), 0 = mma.sync flash attention (cross-check);
+ * "enc_pdl" 1 = encoder kernels under programmatic dependent launch (default), 0 = plain stream-ordered launches;
+ * "profile" 1 = record the stage timeline below. */
 int wm_set_option(wm_handle* h, const char* key, int32_t value);
 /* Debug: per-stage timeline of the last persistent iteration (after wm_set_option(h, "profile", 1)).
  * Rows of 24 int64: stage id, mode, layer; body ns and barrier-wait ns seen by the last CTA; then the
