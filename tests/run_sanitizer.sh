@@ -12,10 +12,10 @@ set -u
 mkdir -p gpurun_out
 export WM_SAN_ITERS=${WM_SAN_ITERS:-4}
 rc=0
-for tool in memcheck synccheck racecheck; do
+for tool in ${WM_SAN_TOOLS:-memcheck synccheck racecheck}; do
   log=gpurun_out/sanitizer_${tool}.log
   echo "== compute-sanitizer --tool $tool" | tee $log
-  timeout 420 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 77 \
+  timeout ${WM_SAN_TIMEOUT:-420} compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 77 \
       python tests/gpu_sanitize_target.py >> $log 2>&1
   r=$?
   echo "== exit code $r" | tee -a $log
