@@ -147,6 +147,10 @@ void* wm_weights_device_ptr(wm_handle* h);
  * "enc_pdl" 1 = encoder kernels under programmatic dependent launch (default), 0 = plain stream-ordered launches;
  * "profile" 1 = record the stage timeline below. */
 int wm_set_option(wm_handle* h, const char* key, int32_t value);
+/* Host logic, no GPU needed: the tile {rows, columns, ring stages} the tcgen05 encoder GEMM runs an M x N x K product
+ * with on a GPU of n_sm SMs (0: 148) -- the shape with the fewest operand bytes on the busiest SM.
+ * fp16_out: the bias / bias+GELU epilogues; 0: the fp32 residual-stream epilogues (128-row tiles only). */
+int wm_enc_gemm_tile(int32_t M, int32_t N, int32_t K, int32_t fp16_out, int32_t n_sm, int32_t* out3);
 /* Debug: per-stage timeline of the last persistent iteration (after wm_set_option(h, "profile", 1)).
  * Rows of 24 int64: stage id, mode, layer; body ns and barrier-wait ns seen by the last CTA; then the
  * 16 raw probes of CTA 0 -- ns offsets from stage begin ([1] end of body, [2] end of barrier, [7] record

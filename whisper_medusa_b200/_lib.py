@@ -59,6 +59,7 @@ SYMBOLS = {
     "wm_last_launches": (C.c_int64, [C.c_void_p, C.c_int32]),
     "wm_set_decode_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "wm_weights_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "wm_enc_gemm_tile": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P(C.c_int32)]),
     "wm_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
     "wm_get_stage_profile": (C.c_int, [C.c_void_p, _P(C.c_int64), C.c_int32, _P(C.c_int32)]),
 }

@@ -22,6 +22,7 @@
 // stride, no im2col buffer exists.
 #include <cuda.h>
 
+#include <cstring>
 #include <map>
 #include <tuple>
 
@@ -330,6 +331,14 @@ static TcTile pick_tile(const EncGemmArgs& g, int n_sm) {
     if (ct < c) { c = ct; best = t; }
   }
   return best;
+}
+
+void enc_gemm_tc_tile(int M, int N, int K, bool fp16_out, int n_sm, int out[3]) {
+  EncGemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.M = M; g.N = N; g.K = K; g.epi = fp16_out ? ENC_EPI_BIAS_F16 : ENC_EPI_BIAS_RES_F32;
+  const TcTile t = pick_tile(g, n_sm > 0 ? n_sm : 148);
+  out[0] = t.mb * TC_BM; out[1] = t.bn; out[2] = t.stages;
 }
 
 // `a_rows` = rows of the A view that may be touched (the allocation is padded accordingly)

@@ -1029,4 +1029,11 @@ extern "C" int wm_set_decode_mode(wm_handle* h, int32_t mode) {
 }
 // Device address of the packed weights (so that further handles on the same GPU can wm_adopt_weights them: one copy
 // of the 3.1 GB blob serves every concurrent stream).
+extern "C" int wm_enc_gemm_tile(int32_t M, int32_t N, int32_t K, int32_t fp16_out, int32_t n_sm, int32_t* out3) {
+  if (!out3 || M <= 0 || N <= 0 || K <= 0 || N % 128 != 0) return WM_ERR_INVALID;
+  int t[3];
+  enc_gemm_tc_tile(M, N, K, fp16_out != 0, n_sm, t);
+  out3[0] = t[0]; out3[1] = t[1]; out3[2] = t[2];
+  return WM_OK;
+}
 extern "C" void* wm_weights_device_ptr(wm_handle* h) { return (h && h->wready) ? (void*)h->wdev : nullptr; }

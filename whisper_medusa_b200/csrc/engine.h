@@ -71,6 +71,8 @@ cudaError_t enc_layernorm(const float* x, const float* g, const float* b, __half
 // ---- enc_gemm_tc.cu (tcgen05 + TMA + TMEM) ----
 cudaError_t enc_gemm_tc(const EncGemmArgs& a, int a_rows, cudaStream_t s, int64_t* n_launch);
 cudaError_t enc_gemm_tc_configure();
+// tile shape {rows, columns, ring stages} the tcgen05 GEMM picks for an M x N x K product (host logic only)
+void enc_gemm_tc_tile(int M, int N, int K, bool fp16_out, int n_sm, int out[3]);
 
 // ---- enc_attn.cu ----
 // qkv: fp16 [S_pad, 3d] (q pre-scaled | k | v); out: fp16 [S_pad, d]; full (non-causal) attention over S keys
