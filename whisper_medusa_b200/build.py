@@ -71,7 +71,9 @@ def build(verbose: bool = False, force: bool = False, extra_flags: List[str] = (
     objs = [o for o, _ in results]
     log = "\n".join(l for _, l in results if l)
     if log:
-        with open(os.path.join(OUT_DIR, "ptxas.log"), "a") as f:
+        # register / spill report of this build (a full rebuild starts the file afresh; alternative builds keep their own)
+        log_path = os.path.join(OUT_DIR, "ptxas.log") if obj_dir == OBJ_DIR else os.path.join(obj_dir, "ptxas.log")
+        with open(log_path, "w" if all(l for _, l in results) else "a") as f:
             f.write(log + "\n")
         if verbose:
             print(log)
